@@ -1,0 +1,217 @@
+/*
+ * pcr_b200.h — C-ABI of libpcr_b200.so, the B200-native (sm_100a) replacement for
+ * the ingest/finalize path of BigHippo123/pointcloud-raster ("PCR").
+ *
+ * This is the drop-in boundary: plain C, opaque handles, plain pointers and
+ * sizes, int status codes.  No C++ types, no PyTorch types.  Each entry point
+ * names the reference interface it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the binding a reference maintainer
+ * would add on their side (pybind11 / ctypes).
+ *
+ * Status codes are the values of pcr::StatusCode (include/pcr/core/types.h:118-126).
+ * On any non-zero return, pcr_last_error() holds the message the reference would
+ * have put in Status::message (thread-local, valid until the next call on the
+ * same thread).
+ *
+ * There is NO CPU fallback behind this ABI: exec_mode CPU is NotImplemented, and
+ * a missing / unusable device is a CudaError regardless of gpu_fallback_to_cpu.
+ */
+#ifndef PCR_B200_H
+#define PCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums (numeric values identical to the reference's) ------------------ */
+
+/* pcr::StatusCode, include/pcr/core/types.h:118-126 */
+enum {
+    PCR_OK = 0, PCR_INVALID_ARGUMENT = 1, PCR_OUT_OF_MEMORY = 2, PCR_CUDA_ERROR = 3,
+    PCR_IO_ERROR = 4, PCR_CRS_ERROR = 5, PCR_NOT_IMPLEMENTED = 6
+};
+/* pcr::ReductionType, include/pcr/core/types.h:34-46 (only 0..5 are registered,
+ * src/ops/reduction_registry.cpp:174-186) */
+enum {
+    PCR_SUM = 0, PCR_MAX = 1, PCR_MIN = 2, PCR_AVERAGE = 3, PCR_WEIGHTED_AVERAGE = 4,
+    PCR_COUNT = 5, PCR_MEDIAN = 6, PCR_PERCENTILE = 7, PCR_MOST_RECENT = 8,
+    PCR_PRIORITY_MERGE = 9, PCR_CUSTOM = 10
+};
+/* pcr::GlyphType, include/pcr/engine/glyph.h:10-14 */
+enum { PCR_GLYPH_POINT = 0, PCR_GLYPH_LINE = 1, PCR_GLYPH_GAUSSIAN = 2 };
+/* pcr::ExecutionMode, include/pcr/engine/pipeline.h:39-44 */
+enum { PCR_EXEC_CPU = 0, PCR_EXEC_GPU = 1, PCR_EXEC_AUTO = 2, PCR_EXEC_HYBRID = 3 };
+/* pcr::MemoryLocation, include/pcr/core/types.h:91-95 */
+enum { PCR_MEM_HOST = 0, PCR_MEM_HOST_PINNED = 1, PCR_MEM_DEVICE = 2 };
+/* pcr::DataType, include/pcr/core/types.h:18-26 */
+enum { PCR_F32 = 0, PCR_F64 = 1, PCR_I32 = 2, PCR_U32 = 3, PCR_I16 = 4, PCR_U16 = 5, PCR_U8 = 6 };
+
+/* ---- plain-data mirrors of the reference's config structs ----------------- */
+
+/* Numeric fields of pcr::GridConfig (include/pcr/core/grid_config.h:17-44). */
+typedef struct pcr_grid_desc {
+    double  min_x, min_y, max_x, max_y;   /* GridConfig::bounds */
+    double  cell_size_x, cell_size_y;     /* cell_size_y < 0 = north-up */
+    int32_t width, height;                /* cells; see pcr_grid_compute_dimensions */
+    int32_t tile_width, tile_height;      /* reference tiles (default 4096): they
+                                             define the touched-tile NaN rule and the
+                                             glyph clipping seams, nothing else */
+} pcr_grid_desc;
+
+/* pcr::GlyphSpec (include/pcr/engine/glyph.h:19-43).  NULL or "" channel = default. */
+typedef struct pcr_glyph_desc {
+    int32_t     type;
+    const char *direction_channel;    float default_direction;
+    const char *half_length_channel;  float default_half_length;
+    const char *sigma_x_channel;      float default_sigma_x;
+    const char *sigma_y_channel;      float default_sigma_y;
+    const char *rotation_channel;     float default_rotation;
+    float       max_radius_cells;
+    int32_t     normalize_weights;    /* accepted and ignored, as upstream
+                                         (src/engine/glyph_kernels.cu:169-179) */
+} pcr_glyph_desc;
+
+/* pcr::ReductionSpec (include/pcr/engine/pipeline.h:20-34).  weight_channel,
+ * timestamp_channel and percentile are never read upstream and are not mirrored. */
+typedef struct pcr_reduction_desc {
+    const char    *value_channel;
+    int32_t        type;
+    const char    *output_band_name;  /* NULL/"" => "<value_channel>_<type int>" */
+    pcr_glyph_desc glyph;
+} pcr_reduction_desc;
+
+/* pcr::PipelineConfig (include/pcr/engine/pipeline.h:49-86), hot-path fields,
+ * plus the additive knobs of the new path (all default 0). */
+typedef struct pcr_pipeline_desc {
+    pcr_grid_desc             grid;
+    const pcr_reduction_desc *reductions;
+    int32_t                   num_reductions;
+    int32_t                   exec_mode;            /* CPU => NotImplemented; GPU/Auto/Hybrid => GPU */
+    int32_t                   gpu_fallback_to_cpu;  /* never honoured: no device => CudaError */
+    int32_t                   cuda_device_id;
+    /* --- additive knobs --- */
+    int32_t                   deterministic;        /* 1 = sort-then-segmented-reduce, bit-reproducible */
+    int32_t                   ring_depth;           /* host-ingest staging slots, 0 = default (3) */
+    uint64_t                  ring_slot_points;     /* points per slot, 0 = default (4 Mi) */
+    int32_t                   staging_threads;      /* host copy threads, 0 = default */
+    int32_t                   point_kernel;         /* 0 = auto, 1 = direct LDG, 2 = TMA-staged persistent */
+    int32_t                   warp_aggregate;       /* 0 = auto (adaptive run aggregation), 2 = off */
+    int32_t                   async_ingest;         /* 1 = device-resident ingests return without a
+                                                       stream sync; buffers must stay valid until the
+                                                       next finalize / synchronize */
+} pcr_pipeline_desc;
+
+/* One named channel of a point cloud (pcr::PointCloud, include/pcr/core/point_cloud.h:29-103). */
+typedef struct pcr_channel_view {
+    const char *name;
+    const void *data;     /* count elements; same memory location as x/y */
+    int32_t     dtype;    /* PCR_F32 is the only dtype the pipeline reduces
+                             (src/engine/pipeline.cpp:372-378) */
+} pcr_channel_view;
+
+/* pcr::ProgressInfo (include/pcr/engine/pipeline.h:91-99). */
+typedef struct pcr_progress {
+    uint64_t collections_processed;
+    uint64_t collections_total;    /* always 0 (streaming), as upstream */
+    uint64_t points_processed;     /* counts every ingested point, in-grid or not
+                                      (src/engine/pipeline.cpp:749) */
+    uint64_t tiles_active;         /* reference tiles touched so far */
+    float    elapsed_seconds;
+} pcr_progress;
+
+/* Device-side timings, accumulated since the last pcr_pipeline_profile_reset
+ * while profiling is enabled (CUDA events on the launching stream). */
+typedef struct pcr_profile {
+    double   accumulate_ms;     uint64_t accumulate_launches;  /* route+accumulate / glyph kernels */
+    double   sort_ms;           uint64_t sort_launches;        /* deterministic mode: key build + radix sort */
+    double   finalize_ms;       uint64_t finalize_launches;    /* finalize (+merge) kernels */
+    double   init_ms;           uint64_t init_launches;        /* state identity fill */
+    uint64_t h2d_bytes;         uint64_t d2h_bytes;            /* bytes moved by ingest ring / finalize */
+    uint64_t points;                                           /* points fed to accumulate kernels */
+} pcr_profile;
+
+typedef struct pcr_pipeline pcr_pipeline;
+typedef int (*pcr_progress_fn)(const pcr_progress *info, void *user);  /* return 0 to cancel */
+
+/* ---- errors / devices ------------------------------------------------------ */
+const char *pcr_last_error(void);
+int  pcr_device_count(void);                                  /* cuda_device_count, types.h:157-169 */
+int  pcr_device_name(int device, char *buf, size_t buflen);   /* cuda_device_name, types.h:171-184 */
+int  pcr_device_mem_info(int device, uint64_t *free_bytes, uint64_t *total_bytes); /* types.h:186-201 */
+const char *pcr_version(void);
+
+/* ---- GridConfig host logic ------------------------------------------------- */
+/* GridConfig::compute_dimensions, src/core/grid_config.cpp:7-22 */
+int pcr_grid_compute_dimensions(pcr_grid_desc *grid);
+/* GridConfig::world_to_cell, src/core/grid_config.cpp:24-43; returns 1 if inside */
+int pcr_grid_world_to_cell(const pcr_grid_desc *grid, double wx, double wy,
+                           int32_t *col, int32_t *row);
+
+/* ---- memory for PointCloud buffers (PointCloud::create/to, point_cloud.cpp:37-90,404-512) */
+int pcr_mem_alloc(int location, int device, size_t bytes, void **out);
+int pcr_mem_free(int location, int device, void *ptr);
+int pcr_mem_copy(void *dst, int dst_location, const void *src, int src_location,
+                 size_t bytes, int device);
+
+/* ---- Pipeline (include/pcr/engine/pipeline.h:105-145) ---------------------- */
+/* Pipeline::create + Impl::initialize, src/engine/pipeline.cpp:92-281,1294-1304.
+ * On failure *out is NULL (the reference returns nullptr) and the code/message say why. */
+int pcr_pipeline_create(const pcr_pipeline_desc *desc, pcr_pipeline **out);
+void pcr_pipeline_destroy(pcr_pipeline *p);
+/* Pipeline::validate, src/engine/pipeline.cpp:1306-1338 */
+int pcr_pipeline_validate(const pcr_pipeline *p);
+/* Pipeline::ingest -> Impl::process_cloud, src/engine/pipeline.cpp:283-770,1340.
+ * Borrowed pointers; `location` says where x/y/channels live (host pageable, host
+ * pinned or device).  Returns once the caller may free or overwrite the buffers. */
+int pcr_pipeline_ingest(pcr_pipeline *p, const double *x, const double *y, size_t count,
+                        const pcr_channel_view *channels, int32_t num_channels,
+                        int32_t location);
+/* Pipeline::finalize -> Impl::finalize_result, src/engine/pipeline.cpp:1154-1286,1344.
+ * Finalizes on the device and copies every band to host memory owned by the
+ * pipeline.  May be called repeatedly; later ingests keep accumulating. */
+int pcr_pipeline_finalize(pcr_pipeline *p);
+/* Same, but leaves the finalized bands in HBM only (no D2H). */
+int pcr_pipeline_finalize_device(pcr_pipeline *p);
+/* Pipeline::result()->band_f32(i), include/pcr/core/grid.h:62-66: row-major
+ * rows x cols float32, valid until the next finalize/destroy. */
+int pcr_pipeline_result_band(pcr_pipeline *p, int32_t band, const float **data,
+                             int32_t *rows, int32_t *cols);
+int pcr_pipeline_result_band_device(pcr_pipeline *p, int32_t band, const float **device_data,
+                                    int32_t *rows, int32_t *cols);
+/* Band name: output_band_name or "<value_channel>_<type>", pipeline.cpp:1178-1180 */
+int pcr_pipeline_band_name(const pcr_pipeline *p, int32_t band, char *buf, size_t buflen);
+/* Pipeline::stats, src/engine/pipeline.cpp:1388-1401 */
+int pcr_pipeline_stats(const pcr_pipeline *p, pcr_progress *out);
+/* Pipeline::set_progress_callback, src/engine/pipeline.cpp:1380-1382.  Fires
+ * synchronously on the caller's thread after each ingest; returning 0 makes that
+ * ingest fail with "pipeline: cancelled by user" (pipeline.cpp:753-767). */
+int pcr_pipeline_set_progress_callback(pcr_pipeline *p, pcr_progress_fn fn, void *user);
+/* Drop all accumulated state (what deleting state_dir + re-creating does upstream). */
+int pcr_pipeline_reset(pcr_pipeline *p);
+/* Block until all device work of this pipeline is complete. */
+int pcr_pipeline_synchronize(pcr_pipeline *p);
+
+/* ---- profiling (new; feeds bench.py's roofline block) ---------------------- */
+int pcr_pipeline_profile_enable(pcr_pipeline *p, int32_t on);
+int pcr_pipeline_profile_reset(pcr_pipeline *p);
+int pcr_pipeline_profile_read(pcr_pipeline *p, pcr_profile *out);
+
+/* ---- multi-GPU: one process per GPU, point shards, combine at finalize ----- */
+/* The partial grid states of all ranks are merged with Op::merge semantics
+ * (include/pcr/ops/builtin_ops.h:15,28,41,54,67,95-97; src/engine/grid_merge.cu:26-35)
+ * over NCCL: each rank owns a row slice, receives every peer's partial slice,
+ * merges them in rank order and finalizes the slice in one kernel; slices are then
+ * gathered so that every rank's result bands are complete.
+ * pcr_comm_unique_id: rank 0 fills 128 bytes (ncclUniqueId) and ships them to the
+ * other ranks by any side channel (bench.py uses torch.distributed). */
+int pcr_comm_unique_id(void *id128);
+int pcr_pipeline_comm_init(pcr_pipeline *p, const void *id128, int32_t rank, int32_t world_size);
+int pcr_pipeline_comm_barrier(pcr_pipeline *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCR_B200_H */

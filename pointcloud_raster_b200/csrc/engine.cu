@@ -1,0 +1,760 @@
+// engine.cu — host orchestration of the B200 ingest/finalize path.
+// See engine.h for the design; reference counterparts are cited per function.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace pcrb {
+
+#define CU_TRY(expr)                                                                     \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return Status::error(PCR_CUDA_ERROR, std::string("CUDA error: ") +           \
+                                 cudaGetErrorString(_e) + " (" #expr ")");               \
+    } while (0)
+
+#define ST_TRY(expr)                        \
+    do {                                    \
+        Status _s = (expr);                 \
+        if (!_s.ok()) return _s;            \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// CopyPool
+// ---------------------------------------------------------------------------
+CopyPool::CopyPool(int threads)
+{
+    const int extra = std::max(0, threads - 1);
+    jobs_.resize(extra);
+    for (int i = 0; i < extra; ++i) workers_.emplace_back(&CopyPool::worker, this, i);
+}
+
+CopyPool::~CopyPool()
+{
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+        ++generation_;
+    }
+    cv_start_.notify_all();
+    for (auto& t : workers_) t.join();
+}
+
+void CopyPool::worker(int idx)
+{
+    uint64_t seen = 0;
+    for (;;) {
+        Job job;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_start_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            if (stop_) return;
+            job = jobs_[idx];
+        }
+        if (job.bytes) std::memcpy(job.dst, job.src, job.bytes);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) cv_done_.notify_one();
+        }
+    }
+}
+
+void CopyPool::copy(void* dst, const void* src, size_t bytes)
+{
+    const int parts = static_cast<int>(workers_.size()) + 1;
+    if (parts == 1 || bytes < (1u << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t chunk = align_up((bytes + parts - 1) / parts, 4096);
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (int i = 0; i < parts - 1; ++i) {
+            const size_t off = std::min(bytes, chunk * (i + 1));
+            const size_t len = std::min(chunk, bytes - off);
+            jobs_[i] = {static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len};
+        }
+        pending_ = parts - 1;
+        ++generation_;
+    }
+    cv_start_.notify_all();
+    std::memcpy(dst, src, std::min(bytes, chunk));
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+}
+
+// ---------------------------------------------------------------------------
+// Planning
+// ---------------------------------------------------------------------------
+bool GlyphSpecHost::same_footprint(const GlyphSpecHost& o) const
+{
+    if (type != o.type) return false;
+    if (type == PCR_GLYPH_POINT) return true;
+    auto feq = [](float a, float b) { return std::memcmp(&a, &b, sizeof(float)) == 0; };
+    if (!feq(max_radius_cells, o.max_radius_cells)) return false;
+    if (type == PCR_GLYPH_LINE)
+        return direction_channel == o.direction_channel &&
+               half_length_channel == o.half_length_channel &&
+               feq(default_direction, o.default_direction) &&
+               feq(default_half_length, o.default_half_length);
+    return sigma_x_channel == o.sigma_x_channel && sigma_y_channel == o.sigma_y_channel &&
+           rotation_channel == o.rotation_channel && feq(default_sigma_x, o.default_sigma_x) &&
+           feq(default_sigma_y, o.default_sigma_y) && feq(default_rotation, o.default_rotation);
+}
+
+static bool power_of_two(double v)
+{
+    int e;
+    return std::isfinite(v) && v != 0.0 && std::frexp(std::fabs(v), &e) == 0.5;
+}
+
+static int record_width(int words) { return words <= 1 ? 1 : words <= 2 ? 2 : words <= 4 ? 4 : 8; }
+
+namespace {
+// Tries to place reduction `r` (index `band`) into pass `p`; false if it does not fit.
+bool place(Pass& p, const ReductionHost& r, int band)
+{
+    PassLayout L = p.layout;
+    std::vector<std::string> chans = p.channels;
+    FinalizeProgram fin = p.fin;
+    if (fin.n >= kMaxBandsPerPass) return false;
+
+    auto chan_of = [&](const std::string& name) -> int {
+        for (size_t i = 0; i < chans.size(); ++i)
+            if (chans[i] == name) return static_cast<int>(i);
+        if (static_cast<int>(chans.size()) >= kMaxChan) return -2;
+        chans.push_back(name);
+        return static_cast<int>(chans.size()) - 1;
+    };
+    auto add_word = [&](int src) -> int {   // src = channel slot, or -1 for the count/weight word
+        for (int j = 0; j < L.n_add; ++j)
+            if (L.add_src[j] == src) return j;
+        if (L.n_add >= kMaxAdd) return -2;
+        L.add_src[L.n_add] = static_cast<int8_t>(src);
+        return L.n_add++;
+    };
+    auto ext_word = [&](int8_t* srcs, int& n, int src) -> int {
+        for (int j = 0; j < n; ++j)
+            if (srcs[j] == src) return j;
+        if (n >= kMaxExt) return -2;
+        srcs[n] = static_cast<int8_t>(src);
+        return n++;
+    };
+
+    // Words are recorded by (kind, index-within-kind); absolute word offsets are
+    // fixed up when the pass is sealed, because n_add / n_max may still grow.
+    int kind = 0, a = -1, b = -1;
+    const bool needs_value = r.type != PCR_COUNT;
+    int c = -1;
+    if (needs_value) {
+        c = chan_of(r.value_channel);
+        if (c == -2) return false;
+    }
+    switch (r.type) {
+    case PCR_SUM:     kind = FIN_SUM;   a = add_word(c); break;
+    case PCR_COUNT:   kind = FIN_COUNT; a = add_word(-1); break;
+    case PCR_AVERAGE:
+    case PCR_WEIGHTED_AVERAGE:
+                      kind = FIN_RATIO; a = add_word(c); b = add_word(-1); break;
+    case PCR_MAX:     kind = FIN_MAX;   a = ext_word(L.max_src, L.n_max, c); break;
+    case PCR_MIN:     kind = FIN_MIN;   a = ext_word(L.min_src, L.n_min, c); break;
+    default: return false;
+    }
+    if (a == -2 || b == -2) return false;
+    if (L.n_add + L.n_max + L.n_min > 8) return false;
+
+    fin.kind[fin.n] = kind;
+    fin.word_a[fin.n] = a;    // index within its kind for now
+    fin.word_b[fin.n] = b;
+    fin.band[fin.n] = band;
+    ++fin.n;
+    L.n_chan = static_cast<int>(chans.size());
+    p.layout = L;
+    p.channels = chans;
+    p.fin = fin;
+    return true;
+}
+
+void seal(Pass& p)
+{
+    PassLayout& L = p.layout;
+    L.width = record_width(L.n_add + L.n_max + L.n_min);
+    for (int i = 0; i < p.fin.n; ++i) {
+        if (p.fin.kind[i] == FIN_MAX) p.fin.word_a[i] += L.n_add;
+        if (p.fin.kind[i] == FIN_MIN) p.fin.word_a[i] += L.n_add + L.n_max;
+    }
+}
+}  // namespace
+
+Status Engine::plan()
+{
+    passes_.clear();
+    std::vector<bool> placed(reductions_.size(), false);
+    for (size_t i = 0; i < reductions_.size(); ++i) {
+        ReductionHost& r = reductions_[i];
+        if (r.glyph.type != PCR_GLYPH_POINT && (r.type == PCR_MAX || r.type == PCR_MIN)) {
+            r.rejected = true;
+            placed[i] = true;
+        }
+    }
+    for (size_t i = 0; i < reductions_.size(); ++i) {
+        if (placed[i]) continue;
+        Pass p;
+        p.glyph = reductions_[i].glyph;
+        std::memset(&p.layout, 0, sizeof(p.layout));
+        std::memset(&p.fin, 0, sizeof(p.fin));
+        for (size_t j = i; j < reductions_.size(); ++j) {
+            if (placed[j] || !reductions_[j].glyph.same_footprint(p.glyph)) continue;
+            if (place(p, reductions_[j], static_cast<int>(j))) placed[j] = true;
+        }
+        seal(p);
+        passes_.push_back(std::move(p));
+    }
+    // every channel any pass reads, value channels first
+    all_channels_.clear();
+    auto want = [&](const std::string& name) {
+        if (name.empty()) return;
+        if (std::find(all_channels_.begin(), all_channels_.end(), name) == all_channels_.end())
+            all_channels_.push_back(name);
+    };
+    for (const Pass& p : passes_) for (const auto& c : p.channels) want(c);
+    for (const Pass& p : passes_) {
+        if (p.glyph.type == PCR_GLYPH_LINE) { want(p.glyph.direction_channel); want(p.glyph.half_length_channel); }
+        if (p.glyph.type == PCR_GLYPH_GAUSSIAN) { want(p.glyph.sigma_x_channel); want(p.glyph.sigma_y_channel); want(p.glyph.rotation_channel); }
+    }
+    return Status::success();
+}
+
+int Engine::channel_slot(const std::string& name)
+{
+    for (size_t i = 0; i < all_channels_.size(); ++i)
+        if (all_channels_[i] == name) return static_cast<int>(i);
+    return -1;
+}
+
+// ---------------------------------------------------------------------------
+// create / destroy   (Pipeline::create + Impl::initialize, pipeline.cpp:92-281,1294-1304)
+// ---------------------------------------------------------------------------
+Status Engine::create(const pcr_pipeline_desc& desc, Engine** out)
+{
+    *out = nullptr;
+    Engine* e = new Engine();
+    Status s = e->init(desc);
+    if (!s.ok()) { delete e; return s; }
+    *out = e;
+    return s;
+}
+
+Status Engine::init(const pcr_pipeline_desc& d)
+{
+    t0_ = std::chrono::steady_clock::now();
+    grid_ = d.grid;
+    exec_mode_ = d.exec_mode;
+    device_ = d.cuda_device_id;
+    deterministic_ = d.deterministic != 0;
+    async_device_ingest_ = d.async_ingest != 0;
+    point_variant_ = d.point_kernel == 2 ? POINT_TMA : d.point_kernel == 1 ? POINT_DIRECT : POINT_DIRECT;
+    warp_aggregate_ = d.warp_aggregate != 2;
+    slot_points_ = d.ring_slot_points ? static_cast<size_t>(d.ring_slot_points) : (size_t(1) << 20);
+    slot_points_ = align_up(slot_points_, 1024);
+    const int depth = d.ring_depth > 0 ? d.ring_depth : 3;
+    ring_.resize(depth);
+    staging_threads_ = d.staging_threads > 0 ? d.staging_threads
+                                             : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+
+    if (exec_mode_ == PCR_EXEC_CPU)
+        return Status::error(PCR_NOT_IMPLEMENTED,
+                             "pipeline: ExecutionMode.CPU is not available on the B200 path "
+                             "(GPU-only; there is no CPU fallback)");
+    if (exec_mode_ != PCR_EXEC_GPU && exec_mode_ != PCR_EXEC_AUTO && exec_mode_ != PCR_EXEC_HYBRID)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: unknown execution mode");
+
+    // reductions (registry check: src/ops/reduction_registry.cpp:174-186 -> "unknown reduction type")
+    for (int i = 0; i < d.num_reductions; ++i) {
+        const pcr_reduction_desc& r = d.reductions[i];
+        ReductionHost h;
+        h.value_channel = r.value_channel ? r.value_channel : "";
+        h.type = r.type;
+        if (h.type < PCR_SUM || h.type > PCR_COUNT)
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: unknown reduction type");
+        h.band_name = (r.output_band_name && r.output_band_name[0])
+                          ? r.output_band_name
+                          : h.value_channel + "_" + std::to_string(h.type);   // pipeline.cpp:1178-1180
+        auto str = [](const char* s) { return std::string(s ? s : ""); };
+        h.glyph.type = r.glyph.type;
+        if (h.glyph.type < PCR_GLYPH_POINT || h.glyph.type > PCR_GLYPH_GAUSSIAN)
+            return Status::error(PCR_NOT_IMPLEMENTED, "glyph: unknown glyph type");
+        h.glyph.direction_channel = str(r.glyph.direction_channel);
+        h.glyph.half_length_channel = str(r.glyph.half_length_channel);
+        h.glyph.sigma_x_channel = str(r.glyph.sigma_x_channel);
+        h.glyph.sigma_y_channel = str(r.glyph.sigma_y_channel);
+        h.glyph.rotation_channel = str(r.glyph.rotation_channel);
+        h.glyph.default_direction = r.glyph.default_direction;
+        h.glyph.default_half_length = r.glyph.default_half_length;
+        h.glyph.default_sigma_x = r.glyph.default_sigma_x;
+        h.glyph.default_sigma_y = r.glyph.default_sigma_y;
+        h.glyph.default_rotation = r.glyph.default_rotation;
+        h.glyph.max_radius_cells = r.glyph.max_radius_cells;
+        reductions_.push_back(std::move(h));
+    }
+
+    if (grid_.width <= 0 || grid_.height <= 0)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: grid dimensions must be positive");
+    if (grid_.tile_width <= 0 || grid_.tile_height <= 0)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: tile dimensions must be positive");
+    cells_ = static_cast<size_t>(grid_.width) * static_cast<size_t>(grid_.height);
+    // the reference stores the global cell index as u32 (tile_router.cpp:111-112)
+    if (cells_ >= (size_t(1) << 32))
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: grid has 2^32 or more cells");
+
+    gp_.min_x = grid_.min_x; gp_.max_x = grid_.max_x; gp_.min_y = grid_.min_y; gp_.max_y = grid_.max_y;
+    gp_.csx = grid_.cell_size_x; gp_.csy = grid_.cell_size_y;
+    gp_.inv_csx = 1.0 / grid_.cell_size_x; gp_.inv_csy = 1.0 / grid_.cell_size_y;
+    gp_.width = grid_.width; gp_.height = grid_.height;
+    gp_.tile_w = grid_.tile_width; gp_.tile_h = grid_.tile_height;
+    gp_.tiles_x = (grid_.width + grid_.tile_width - 1) / grid_.tile_width;
+    gp_.tiles_y = (grid_.height + grid_.tile_height - 1) / grid_.tile_height;
+    gp_.exact_x = power_of_two(grid_.cell_size_x);
+    gp_.exact_y = power_of_two(grid_.cell_size_y);
+    n_tiles_ = gp_.tiles_x * gp_.tiles_y;
+
+    // device (no fallback: gpu_fallback_to_cpu is never honoured on this path)
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count <= 0)
+        return Status::error(PCR_CUDA_ERROR,
+                             "No CUDA-capable GPU detected - the B200 path has no CPU fallback"
+                             " (gpu_fallback_to_cpu is not honoured)");
+    if (device_ < 0 || device_ >= count)
+        return Status::error(PCR_CUDA_ERROR, "pipeline: cuda_device_id out of range");
+    CU_TRY(cudaSetDevice(device_));
+    cudaDeviceProp prop{};
+    CU_TRY(cudaGetDeviceProperties(&prop, device_));
+    sm_count_ = prop.multiProcessorCount;
+    if (prop.major < 10)
+        return Status::error(PCR_CUDA_ERROR, std::string("pipeline: device '") + prop.name +
+                             "' is not sm_100-class; this library carries sm_100a code only");
+    CU_TRY(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
+
+    ST_TRY(plan());
+    if (deterministic_)
+        for (const Pass& p : passes_)
+            if (p.glyph.type != PCR_GLYPH_POINT)
+                return Status::error(PCR_NOT_IMPLEMENTED,
+                                     "pipeline: deterministic mode covers the Point glyph only");
+    ST_TRY(alloc_state());
+    ST_TRY(init_state());
+    CU_TRY(cudaStreamSynchronize(compute_));
+    return Status::success();
+}
+
+Status Engine::alloc_state()
+{
+    for (Pass& p : passes_)
+        CU_TRY(cudaMalloc(&p.d_state, cells_ * p.layout.width * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&d_touched_, std::max(1, n_tiles_) * sizeof(uint32_t)));
+    const size_t out_bytes = std::max<size_t>(1, reductions_.size()) * cells_ * sizeof(float);
+    CU_TRY(cudaMalloc(&d_out_, out_bytes));
+    return Status::success();
+}
+
+Status Engine::init_state()
+{
+    prof_begin(PROF_INIT, compute_);
+    for (Pass& p : passes_) CU_TRY(launch_init_state(compute_, p.d_state, cells_, p.layout));
+    CU_TRY(cudaMemsetAsync(d_touched_, 0, std::max(1, n_tiles_) * sizeof(uint32_t), compute_));
+    prof_end(compute_);
+    return Status::success();
+}
+
+Status Engine::reset()
+{
+    CU_TRY(cudaSetDevice(device_));
+    ST_TRY(synchronize());
+    ST_TRY(init_state());
+    collections_ = 0;
+    points_ = 0;
+    finalized_ = false;
+    return synchronize();
+}
+
+Status Engine::synchronize()
+{
+    CU_TRY(cudaSetDevice(device_));
+    CU_TRY(cudaStreamSynchronize(copy_));
+    CU_TRY(cudaStreamSynchronize(compute_));
+    return Status::success();
+}
+
+Engine::~Engine()
+{
+    if (compute_ || copy_) {
+        cudaSetDevice(device_);
+        if (copy_) cudaStreamSynchronize(copy_);
+        if (compute_) cudaStreamSynchronize(compute_);
+    }
+    if (comm_) engine_comm_destroy(nccl_, comm_);
+    for (Pass& p : passes_) { cudaFree(p.d_state); cudaFree(p.d_combined); }
+    cudaFree(d_touched_);
+    cudaFree(d_touched_all_);
+    cudaFree(d_out_);
+    if (h_out_) cudaFreeHost(h_out_);
+    for (Slot& s : ring_) {
+        if (s.h) cudaFreeHost(s.h);
+        cudaFree(s.d);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.kernel_done) cudaEventDestroy(s.kernel_done);
+    }
+    cudaFree(d_sort_tmp_); cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_idx_); cudaFree(d_idx_alt_);
+    for (auto& sp : prof_open_) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto& ev : prof_free_) cudaEventDestroy(ev);
+    delete pool_;
+    if (compute_) cudaStreamDestroy(compute_);
+    if (copy_) cudaStreamDestroy(copy_);
+}
+
+// Pipeline::validate, src/engine/pipeline.cpp:1306-1338
+Status Engine::validate() const
+{
+    if (grid_.width <= 0 || grid_.height <= 0)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: grid dimensions must be positive");
+    if (grid_.tile_width <= 0 || grid_.tile_height <= 0)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: tile dimensions must be positive");
+    if (reductions_.empty())
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: at least one reduction must be specified");
+    for (const auto& r : reductions_) {
+        if (r.value_channel.empty())
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: value_channel must be specified");
+        if (r.type < PCR_SUM || r.type > PCR_COUNT)
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: unknown reduction type");
+    }
+    return Status::success();
+}
+
+// ---------------------------------------------------------------------------
+// profiling
+// ---------------------------------------------------------------------------
+void Engine::prof_begin(ProfKind k, cudaStream_t s)
+{
+    if (!prof_on_) return;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!prof_free_.empty()) { e = prof_free_.back(); prof_free_.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    };
+    prof_cur_ = {get(), get(), k};
+    cudaEventRecord(prof_cur_.a, s);
+}
+
+void Engine::prof_end(cudaStream_t s)
+{
+    if (!prof_on_) return;
+    cudaEventRecord(prof_cur_.b, s);
+    prof_open_.push_back(prof_cur_);
+    ++prof_n_[prof_cur_.k];
+}
+
+Status Engine::prof_collect()
+{
+    for (auto& sp : prof_open_) {
+        CU_TRY(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        prof_ms_[sp.k] += ms;
+        prof_free_.push_back(sp.a);
+        prof_free_.push_back(sp.b);
+    }
+    prof_open_.clear();
+    return Status::success();
+}
+
+Status Engine::profile_enable(bool on) { CU_TRY(cudaSetDevice(device_)); prof_on_ = on; return Status::success(); }
+
+Status Engine::profile_reset()
+{
+    CU_TRY(cudaSetDevice(device_));
+    ST_TRY(prof_collect());
+    for (int k = 0; k < PROF_KINDS; ++k) { prof_ms_[k] = 0; prof_n_[k] = 0; }
+    prof_h2d_ = prof_d2h_ = prof_points_ = 0;
+    return Status::success();
+}
+
+Status Engine::profile_read(pcr_profile& o)
+{
+    CU_TRY(cudaSetDevice(device_));
+    ST_TRY(prof_collect());
+    o.accumulate_ms = prof_ms_[PROF_ACC];  o.accumulate_launches = prof_n_[PROF_ACC];
+    o.sort_ms = prof_ms_[PROF_SORT];       o.sort_launches = prof_n_[PROF_SORT];
+    o.finalize_ms = prof_ms_[PROF_FIN];    o.finalize_launches = prof_n_[PROF_FIN];
+    o.init_ms = prof_ms_[PROF_INIT];       o.init_launches = prof_n_[PROF_INIT];
+    o.h2d_bytes = prof_h2d_; o.d2h_bytes = prof_d2h_; o.points = prof_points_;
+    return Status::success();
+}
+
+// ---------------------------------------------------------------------------
+// ingest   (Pipeline::ingest -> Impl::process_cloud, pipeline.cpp:283-770)
+// ---------------------------------------------------------------------------
+Status Engine::ingest(const double* x, const double* y, size_t n, const pcr_channel_view* chans,
+                      int nchans, int location)
+{
+    if (n == 0) return Status::success();                       // pipeline.cpp:284-287
+    if (!x || !y) return Status::error(PCR_INVALID_ARGUMENT, "pipeline: null coordinate arrays");
+    CU_TRY(cudaSetDevice(device_));
+
+    auto find = [&](const std::string& name) -> const pcr_channel_view* {
+        for (int i = 0; i < nchans; ++i)
+            if (chans[i].name && name == chans[i].name) return &chans[i];
+        return nullptr;
+    };
+    // value channels must exist and be Float32 (pipeline.cpp:365-378); checked for
+    // every reduction BEFORE any work, so a failing ingest leaves the state untouched
+    // (the reference would already have folded the reductions listed earlier).
+    for (const auto& r : reductions_) {
+        const pcr_channel_view* v = find(r.value_channel);
+        if (!v || !v->data)
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: value channel not found: " + r.value_channel);
+        if (v->dtype != PCR_F32)
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: value channel must be Float32");
+    }
+    for (const auto& r : reductions_)
+        if (r.rejected)
+            return Status::error(PCR_NOT_IMPLEMENTED,
+                                 "pipeline: glyph splatting only supports WeightedAverage, Average, "
+                                 "Sum, or Count reduction types");
+
+    // pointer per planned channel; glyph channels that are absent or not Float32
+    // silently fall back to the default (pipeline.cpp:551-560)
+    std::vector<const float*> ptrs(all_channels_.size(), nullptr);
+    for (size_t i = 0; i < all_channels_.size(); ++i) {
+        const pcr_channel_view* v = find(all_channels_[i]);
+        if (v && v->data && v->dtype == PCR_F32) ptrs[i] = static_cast<const float*>(v->data);
+    }
+
+    Status s;
+    if (location == PCR_MEM_DEVICE) s = ingest_device(x, y, n, ptrs);
+    else if (location == PCR_MEM_HOST || location == PCR_MEM_HOST_PINNED)
+        s = ingest_host(x, y, n, ptrs, location == PCR_MEM_HOST_PINNED);
+    else return Status::error(PCR_INVALID_ARGUMENT, "pipeline: unknown memory location");
+    ST_TRY(s);
+
+    points_ += n;            // counts every ingested point (pipeline.cpp:749)
+    ++collections_;
+    finalized_ = false;
+
+    if (progress_fn_) {
+        pcr_progress info{};
+        ST_TRY(stats(info));
+        if (!progress_fn_(&info, progress_user_))
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: cancelled by user");   // pipeline.cpp:762-766
+    }
+    return Status::success();
+}
+
+// Launches every pass over one device-resident chunk on the compute stream.
+Status Engine::run_passes(const double* dx, const double* dy, size_t n,
+                          const std::vector<const float*>& cp)
+{
+    if (deterministic_) return run_passes_deterministic(dx, dy, n, cp);
+    prof_begin(PROF_ACC, compute_);
+    for (Pass& p : passes_) {
+        ChannelPtrs ch{};
+        for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])];
+        if (p.glyph.type == PCR_GLYPH_POINT) {
+            CU_TRY(launch_point_accumulate(compute_, point_variant_, warp_aggregate_, dx, dy, ch, n,
+                                           p.d_state, gp_, p.layout, d_touched_, sm_count_));
+        } else {
+            GlyphParams g{};
+            auto opt = [&](const std::string& name) -> const float* {
+                const int s = name.empty() ? -1 : channel_slot(name);
+                return s < 0 ? nullptr : cp[s];
+            };
+            g.direction = opt(p.glyph.direction_channel);     g.default_direction = p.glyph.default_direction;
+            g.half_length = opt(p.glyph.half_length_channel); g.default_half_length = p.glyph.default_half_length;
+            g.sigma_x = opt(p.glyph.sigma_x_channel);         g.default_sigma_x = p.glyph.default_sigma_x;
+            g.sigma_y = opt(p.glyph.sigma_y_channel);         g.default_sigma_y = p.glyph.default_sigma_y;
+            g.rotation = opt(p.glyph.rotation_channel);       g.default_rotation = p.glyph.default_rotation;
+            g.max_radius_cells = p.glyph.max_radius_cells;
+            if (p.glyph.type == PCR_GLYPH_LINE)
+                CU_TRY(launch_line_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
+            else
+                CU_TRY(launch_gaussian_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
+        }
+    }
+    prof_end(compute_);
+    prof_points_ += n;
+    return Status::success();
+}
+
+Status Engine::ingest_device(const double* x, const double* y, size_t n,
+                             const std::vector<const float*>& cp)
+{
+    ST_TRY(run_passes(x, y, n, cp));
+    if (!async_device_ingest_) CU_TRY(cudaStreamSynchronize(compute_));
+    return Status::success();
+}
+
+Status Engine::ensure_ring()
+{
+    if (ring_[0].d) return Status::success();
+    // slot layout: x | y | channel 0 | channel 1 | ...  each segment 256-B aligned
+    const size_t seg64 = align_up(slot_points_ * 8, 256), seg32 = align_up(slot_points_ * 4, 256);
+    slot_bytes_ = 2 * seg64 + all_channels_.size() * seg32;
+    for (Slot& s : ring_) {
+        CU_TRY(cudaMallocHost(&s.h, slot_bytes_));
+        CU_TRY(cudaMalloc(&s.d, slot_bytes_));
+        CU_TRY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming));
+    }
+    if (!pool_) pool_ = new CopyPool(staging_threads_);
+    return Status::success();
+}
+
+// The CUDA-stream ingest ring: chunk k is staged into pinned slot k%depth by the
+// copy pool (skipped when the caller's memory is already pinned), shipped with
+// cudaMemcpyAsync on the copy stream, and consumed by the pass kernels on the
+// compute stream; events order slot reuse.  Replaces PointCloud::to_device_async +
+// cudaStreamSynchronize (pipeline.cpp:299-327) and Hybrid mode (pipeline.cpp:785-1152).
+Status Engine::ingest_host(const double* x, const double* y, size_t n,
+                           const std::vector<const float*>& cp, bool pinned)
+{
+    ST_TRY(ensure_ring());
+    const size_t seg64 = align_up(slot_points_ * 8, 256), seg32 = align_up(slot_points_ * 4, 256);
+    const size_t nch = all_channels_.size();
+    size_t k = 0;
+    for (size_t p0 = 0; p0 < n; p0 += slot_points_, ++k) {
+        const size_t cnt = std::min(slot_points_, n - p0);
+        Slot& s = ring_[k % ring_.size()];
+        if (s.used) CU_TRY(cudaEventSynchronize(s.kernel_done));   // slot drained by its last kernels
+        s.used = true;
+
+        std::vector<const float*> dptr(nch, nullptr);
+        double* dxp = reinterpret_cast<double*>(s.d);
+        double* dyp = reinterpret_cast<double*>(s.d + seg64);
+        if (pinned) {
+            CU_TRY(cudaMemcpyAsync(dxp, x + p0, cnt * 8, cudaMemcpyHostToDevice, copy_));
+            CU_TRY(cudaMemcpyAsync(dyp, y + p0, cnt * 8, cudaMemcpyHostToDevice, copy_));
+            for (size_t c = 0; c < nch; ++c) {
+                if (!cp[c]) continue;
+                float* dc = reinterpret_cast<float*>(s.d + 2 * seg64 + c * seg32);
+                CU_TRY(cudaMemcpyAsync(dc, cp[c] + p0, cnt * 4, cudaMemcpyHostToDevice, copy_));
+                dptr[c] = dc;
+            }
+        } else {
+            // one contiguous H2D when every segment is present; otherwise per segment
+            pool_->copy(s.h, x + p0, cnt * 8);
+            pool_->copy(s.h + seg64, y + p0, cnt * 8);
+            bool all = true;
+            for (size_t c = 0; c < nch; ++c) {
+                if (!cp[c]) { all = false; continue; }
+                pool_->copy(s.h + 2 * seg64 + c * seg32, cp[c] + p0, cnt * 4);
+                dptr[c] = reinterpret_cast<float*>(s.d + 2 * seg64 + c * seg32);
+            }
+            if (all && cnt == slot_points_) {
+                CU_TRY(cudaMemcpyAsync(s.d, s.h, slot_bytes_, cudaMemcpyHostToDevice, copy_));
+            } else {
+                CU_TRY(cudaMemcpyAsync(dxp, s.h, cnt * 8, cudaMemcpyHostToDevice, copy_));
+                CU_TRY(cudaMemcpyAsync(dyp, s.h + seg64, cnt * 8, cudaMemcpyHostToDevice, copy_));
+                for (size_t c = 0; c < nch; ++c)
+                    if (cp[c])
+                        CU_TRY(cudaMemcpyAsync(s.d + 2 * seg64 + c * seg32, s.h + 2 * seg64 + c * seg32,
+                                               cnt * 4, cudaMemcpyHostToDevice, copy_));
+            }
+        }
+        size_t present = 0;
+        for (size_t c = 0; c < nch; ++c) present += cp[c] ? 1 : 0;
+        prof_h2d_ += cnt * (16 + 4 * present);
+        CU_TRY(cudaEventRecord(s.h2d_done, copy_));
+        CU_TRY(cudaStreamWaitEvent(compute_, s.h2d_done, 0));
+        ST_TRY(run_passes(dxp, dyp, cnt, dptr));
+        CU_TRY(cudaEventRecord(s.kernel_done, compute_));
+    }
+    // the caller may reuse its buffers when we return: staged copies are already
+    // done; direct DMA from pinned caller memory must have completed.
+    if (pinned) CU_TRY(cudaStreamSynchronize(copy_));
+    return Status::success();
+}
+
+// ---------------------------------------------------------------------------
+// finalize   (Pipeline::finalize -> Impl::finalize_result, pipeline.cpp:1154-1286)
+// ---------------------------------------------------------------------------
+Status Engine::finalize(bool to_host)
+{
+    CU_TRY(cudaSetDevice(device_));
+    if (world_ > 1) ST_TRY(finalize_multi());
+    else ST_TRY(finalize_single());
+    if (to_host) {
+        const size_t bytes = reductions_.size() * cells_ * sizeof(float);
+        if (!h_out_) CU_TRY(cudaMallocHost(&h_out_, std::max<size_t>(bytes, 4)));
+        CU_TRY(cudaMemcpyAsync(h_out_, d_out_, bytes, cudaMemcpyDeviceToHost, compute_));
+        prof_d2h_ += bytes;
+    }
+    CU_TRY(cudaStreamSynchronize(compute_));
+    finalized_ = true;
+    return Status::success();
+}
+
+Status Engine::finalize_single()
+{
+    prof_begin(PROF_FIN, compute_);
+    for (size_t i = 0; i < reductions_.size(); ++i)
+        if (reductions_[i].rejected)   // never accumulated: all NaN (0xFFFFFFFF is a NaN)
+            CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), compute_));
+    for (Pass& p : passes_) {
+        StateParts parts{};
+        parts.part[0] = p.d_state;
+        parts.n = 1;
+        CU_TRY(launch_finalize(compute_, parts, 0, 0, cells_, d_out_, cells_, gp_, p.layout, p.fin, d_touched_));
+    }
+    prof_end(compute_);
+    return Status::success();
+}
+
+Status Engine::result_band(int band, const float** data, int* rows, int* cols, bool device)
+{
+    if (!finalized_)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: result requested before finalize()");
+    if (band < 0 || band >= static_cast<int>(reductions_.size()))
+        return Status::error(PCR_INVALID_ARGUMENT, "Invalid band index or data type");
+    if (!device && !h_out_)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: bands were finalized on the device only");
+    *data = (device ? d_out_ : h_out_) + static_cast<size_t>(band) * cells_;
+    *rows = grid_.height;
+    *cols = grid_.width;
+    return Status::success();
+}
+
+Status Engine::band_name(int band, std::string& out) const
+{
+    if (band < 0 || band >= static_cast<int>(reductions_.size()))
+        return Status::error(PCR_INVALID_ARGUMENT, "Invalid band index or data type");
+    out = reductions_[band].band_name;
+    return Status::success();
+}
+
+// Pipeline::stats, pipeline.cpp:1388-1401
+Status Engine::stats(pcr_progress& o)
+{
+    CU_TRY(cudaSetDevice(device_));
+    o.collections_processed = collections_;
+    o.collections_total = 0;
+    o.points_processed = points_;
+    std::vector<uint32_t> t(std::max(1, n_tiles_));
+    CU_TRY(cudaMemcpyAsync(t.data(), d_touched_, t.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, compute_));
+    CU_TRY(cudaStreamSynchronize(compute_));
+    uint64_t active = 0;
+    for (int i = 0; i < n_tiles_; ++i) active += t[i] ? 1 : 0;
+    o.tiles_active = active;
+    o.elapsed_seconds = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0_).count();
+    return Status::success();
+}
+
+}  // namespace pcrb

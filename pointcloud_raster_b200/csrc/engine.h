@@ -1,0 +1,208 @@
+// engine.h — C++ host side of the B200 ingest/finalize path (one GPU per Engine).
+//
+// Mirrors pcr::Pipeline::Impl (src/engine/pipeline.cpp:31-57,92-281) in role, not
+// in structure: there is no TileRouter / TileManager / MemoryPool / Accumulator
+// object chain.  State lives whole-grid in HBM as interleaved records for the life
+// of the pipeline; all reductions sharing a glyph are planned into one fused pass;
+// host clouds stream through a pinned staging ring on a copy stream while kernels
+// run on the compute stream (the replacement for to_device_async + Hybrid mode).
+#pragma once
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/pcr_b200.h"
+#include "kernels.cuh"
+
+namespace pcrb {
+
+struct Status {
+    int code = PCR_OK;
+    std::string message;
+    bool ok() const { return code == PCR_OK; }
+    static Status success() { return {}; }
+    static Status error(int c, std::string m) { return {c, std::move(m)}; }
+};
+
+struct GlyphSpecHost {
+    int type = PCR_GLYPH_POINT;
+    std::string direction_channel, half_length_channel, sigma_x_channel, sigma_y_channel,
+        rotation_channel;
+    float default_direction = 0.f, default_half_length = 1.f, default_sigma_x = 1.f,
+          default_sigma_y = 1.f, default_rotation = 0.f, max_radius_cells = 32.f;
+    bool same_footprint(const GlyphSpecHost& o) const;
+};
+
+struct ReductionHost {
+    std::string value_channel;
+    int type = PCR_SUM;
+    std::string band_name;
+    GlyphSpecHost glyph;
+    bool rejected = false;   // glyph + Max/Min: NotImplemented at ingest (pipeline.cpp:500-508)
+};
+
+// One fused pass: every reduction in it shares the glyph footprint.
+struct Pass {
+    GlyphSpecHost glyph;
+    PassLayout layout{};
+    FinalizeProgram fin{};
+    std::vector<std::string> channels;   // distinct value channels, index = ChannelPtrs slot
+    uint32_t* d_state = nullptr;         // cells * layout.width words
+    uint32_t* d_combined = nullptr;      // multi-GPU: received peer slices
+};
+
+// Fixed-size worker pool for the pageable -> pinned staging copies.
+class CopyPool {
+public:
+    explicit CopyPool(int threads);
+    ~CopyPool();
+    void copy(void* dst, const void* src, size_t bytes);   // parallel memcpy, blocking
+    int threads() const { return static_cast<int>(workers_.size()) + 1; }
+private:
+    struct Job { char* dst; const char* src; size_t bytes; };
+    void worker(int idx);
+    std::vector<std::thread> workers_;
+    std::vector<Job> jobs_;
+    std::mutex mu_;
+    std::condition_variable cv_start_, cv_done_;
+    uint64_t generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+struct NcclApi;   // dlopen'ed subset of NCCL (engine_comm.cu)
+
+class Engine {
+public:
+    static Status create(const pcr_pipeline_desc& desc, Engine** out);
+    ~Engine();
+
+    Status validate() const;
+    Status ingest(const double* x, const double* y, size_t n, const pcr_channel_view* chans,
+                  int nchans, int location);
+    Status finalize(bool to_host);
+    Status result_band(int band, const float** data, int* rows, int* cols, bool device);
+    Status band_name(int band, std::string& out) const;
+    Status stats(pcr_progress& out);
+    void set_progress(pcr_progress_fn fn, void* user) { progress_fn_ = fn; progress_user_ = user; }
+    Status reset();
+    Status synchronize();
+
+    Status profile_enable(bool on);
+    Status profile_reset();
+    Status profile_read(pcr_profile& out);
+
+    Status comm_init(const void* id128, int rank, int world);
+    Status comm_barrier();
+
+private:
+    Engine() = default;
+    Status init(const pcr_pipeline_desc& desc);
+    Status plan();
+    Status alloc_state();
+    Status init_state();
+    Status run_passes(const double* dx, const double* dy, size_t n,
+                      const std::vector<const float*>& chan_ptrs);
+    Status run_passes_deterministic(const double* dx, const double* dy, size_t n,
+                                    const std::vector<const float*>& chan_ptrs);
+    Status ingest_device(const double* x, const double* y, size_t n,
+                         const std::vector<const float*>& chan_ptrs);
+    Status ingest_host(const double* x, const double* y, size_t n,
+                       const std::vector<const float*>& chan_ptrs, bool pinned);
+    Status finalize_single();
+    Status finalize_multi();
+    int channel_slot(const std::string& name);
+
+    // profiling helpers
+    enum ProfKind { PROF_ACC = 0, PROF_SORT = 1, PROF_FIN = 2, PROF_INIT = 3, PROF_KINDS = 4 };
+    void prof_begin(ProfKind k, cudaStream_t s);
+    void prof_end(cudaStream_t s);
+    Status prof_collect();
+
+    // ---- configuration ----
+    pcr_grid_desc grid_{};
+    GridParams gp_{};
+    std::vector<ReductionHost> reductions_;
+    int exec_mode_ = PCR_EXEC_AUTO;
+    int device_ = 0;
+    int sm_count_ = 148;
+    bool deterministic_ = false;
+    bool async_device_ingest_ = false;
+    int point_variant_ = POINT_DIRECT;
+    bool warp_aggregate_ = true;
+    size_t cells_ = 0;
+    int n_tiles_ = 0;
+
+    // ---- plan / state ----
+    std::vector<Pass> passes_;
+    std::vector<std::string> all_channels_;   // every channel any pass reads (value + glyph)
+    uint32_t* d_touched_ = nullptr;
+    uint32_t* d_touched_all_ = nullptr;       // multi-GPU merged flags
+    float* d_out_ = nullptr;                  // [bands][cells]
+    float* h_out_ = nullptr;                  // pinned, [bands][cells]
+    bool finalized_ = false;
+
+    // ---- streams / ring ----
+    cudaStream_t compute_ = nullptr, copy_ = nullptr;
+    struct Slot {
+        char* h = nullptr;   // pinned staging
+        char* d = nullptr;   // device chunk
+        cudaEvent_t h2d_done = nullptr, kernel_done = nullptr;
+        bool used = false;
+    };
+    std::vector<Slot> ring_;
+    size_t slot_points_ = 0;
+    size_t slot_bytes_ = 0;
+    CopyPool* pool_ = nullptr;
+    int staging_threads_ = 0;
+    Status ensure_ring();
+
+    // deterministic-mode scratch
+    void* d_sort_tmp_ = nullptr; size_t sort_tmp_bytes_ = 0;
+    uint32_t *d_keys_ = nullptr, *d_keys_alt_ = nullptr, *d_idx_ = nullptr, *d_idx_alt_ = nullptr;
+    size_t sort_capacity_ = 0;
+    Status ensure_sort_scratch(size_t n);
+
+    // ---- stats / progress ----
+    uint64_t collections_ = 0, points_ = 0;
+    std::chrono::steady_clock::time_point t0_;
+    pcr_progress_fn progress_fn_ = nullptr;
+    void* progress_user_ = nullptr;
+
+    // ---- profiling ----
+    bool prof_on_ = false;
+    struct ProfSpan { cudaEvent_t a, b; ProfKind k; };
+    std::vector<ProfSpan> prof_open_;
+    std::vector<cudaEvent_t> prof_free_;
+    ProfSpan prof_cur_{};
+    double prof_ms_[PROF_KINDS] = {0, 0, 0, 0};
+    uint64_t prof_n_[PROF_KINDS] = {0, 0, 0, 0};
+    uint64_t prof_h2d_ = 0, prof_d2h_ = 0, prof_points_ = 0;
+
+    // ---- multi-GPU ----
+    NcclApi* nccl_ = nullptr;
+    void* comm_ = nullptr;
+    int rank_ = 0, world_ = 1;
+};
+
+// deterministic path (det_kernels.cu)
+size_t det_sort_temp_bytes(size_t n, int key_bits);
+cudaError_t det_build_keys(cudaStream_t s, const double* x, const double* y, size_t n,
+                           const GridParams& g, uint32_t* keys, uint32_t* idx, uint32_t* touched);
+cudaError_t det_sort(cudaStream_t s, void* tmp, size_t tmp_bytes, uint32_t*& keys, uint32_t*& keys_alt,
+                     uint32_t*& idx, uint32_t*& idx_alt, size_t n, int key_bits);
+cudaError_t det_point_reduce(cudaStream_t s, const uint32_t* keys, const uint32_t* idx, size_t n,
+                             const ChannelPtrs& ch, uint32_t* state, const PassLayout& L,
+                             uint32_t invalid_key);
+Status comm_unique_id(void* id128);
+void engine_comm_destroy(NcclApi* api, void* comm);
+
+}  // namespace pcrb

@@ -1,0 +1,241 @@
+// engine_ext.cu — the two optional legs of the Engine:
+//   * deterministic mode (sort -> in-order segmented reduce), and
+//   * the multi-GPU combine at finalize (NCCL transport over NVLink + the fused
+//     merge/finalize kernel).
+#include "engine.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace pcrb {
+
+#define CU_TRY(expr)                                                                     \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return Status::error(PCR_CUDA_ERROR, std::string("CUDA error: ") +           \
+                                 cudaGetErrorString(_e) + " (" #expr ")");               \
+    } while (0)
+#define ST_TRY(expr) do { Status _s = (expr); if (!_s.ok()) return _s; } while (0)
+
+// ---------------------------------------------------------------------------
+// Deterministic mode
+// ---------------------------------------------------------------------------
+static int bits_for(size_t max_value)
+{
+    int b = 1;
+    while ((max_value >> b) != 0) ++b;
+    return b;
+}
+
+Status Engine::ensure_sort_scratch(size_t n)
+{
+    if (n <= sort_capacity_) return Status::success();
+    CU_TRY(cudaStreamSynchronize(compute_));
+    cudaFree(d_sort_tmp_); cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_idx_); cudaFree(d_idx_alt_);
+    d_sort_tmp_ = nullptr; d_keys_ = d_keys_alt_ = d_idx_ = d_idx_alt_ = nullptr;
+    sort_capacity_ = 0;
+    const size_t cap = std::max(n, slot_points_);
+    sort_tmp_bytes_ = det_sort_temp_bytes(cap, bits_for(cells_));
+    CU_TRY(cudaMalloc(&d_sort_tmp_, std::max<size_t>(sort_tmp_bytes_, 16)));
+    CU_TRY(cudaMalloc(&d_keys_, cap * 4));
+    CU_TRY(cudaMalloc(&d_keys_alt_, cap * 4));
+    CU_TRY(cudaMalloc(&d_idx_, cap * 4));
+    CU_TRY(cudaMalloc(&d_idx_alt_, cap * 4));
+    sort_capacity_ = cap;
+    return Status::success();
+}
+
+Status Engine::run_passes_deterministic(const double* dx, const double* dy, size_t n,
+                                        const std::vector<const float*>& cp)
+{
+    // point indices are u32 payloads: split very large device clouds
+    const size_t kMaxChunk = size_t(1) << 30;
+    for (size_t p0 = 0; p0 < n; p0 += kMaxChunk) {
+        const size_t cnt = std::min(kMaxChunk, n - p0);
+        ST_TRY(ensure_sort_scratch(cnt));
+        const int key_bits = bits_for(cells_);   // keys are cell ids, `cells_` marks invalid points
+        prof_begin(PROF_SORT, compute_);
+        CU_TRY(det_build_keys(compute_, dx + p0, dy + p0, cnt, gp_, d_keys_, d_idx_, d_touched_));
+        CU_TRY(det_sort(compute_, d_sort_tmp_, sort_tmp_bytes_, d_keys_, d_keys_alt_, d_idx_, d_idx_alt_,
+                        cnt, key_bits));
+        prof_end(compute_);
+        prof_begin(PROF_ACC, compute_);
+        for (Pass& p : passes_) {
+            ChannelPtrs ch{};
+            for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])] + p0;
+            CU_TRY(det_point_reduce(compute_, d_keys_, d_idx_, cnt, ch, p.d_state, p.layout,
+                                    static_cast<uint32_t>(cells_)));
+        }
+        prof_end(compute_);
+        prof_points_ += cnt;
+    }
+    return Status::success();
+}
+
+// ---------------------------------------------------------------------------
+// NCCL (dlopen'ed: the library must load and run on a single GPU without it)
+// ---------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void** comm, int nranks, UniqueId id, int rank) = nullptr;
+    int (*CommDestroy)(void* comm) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int dtype, int peer, void* comm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int dtype, int peer, void* comm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int dtype, int op, void* comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    // ncclDataType_t / ncclRedOp_t values (nccl.h)
+    static constexpr int kUint32 = 3, kFloat32 = 7, kUint8 = 1;
+    static constexpr int kSum = 0, kMax = 2;
+};
+
+static NcclApi* nccl_load(std::string& err)
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (api.handle) return &api;
+    if (tried) { err = "NCCL library not available"; return nullptr; }
+    tried = true;
+    // libnccl.so.2 resolves to the copy already mapped into the process (e.g. the
+    // one bundled with PyTorch) when there is one, else to the system library.
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return nullptr; }
+    auto sym = [&](const char* n) { return dlsym(api.handle, n); };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.GroupStart || !api.GroupEnd ||
+        !api.Send || !api.Recv || !api.AllReduce || !api.GetErrorString) {
+        err = "libnccl.so.2 lacks a required symbol";
+        api.handle = nullptr;
+        return nullptr;
+    }
+    return &api;
+}
+
+#define NC_TRY(expr)                                                                      \
+    do {                                                                                  \
+        int _r = (expr);                                                                  \
+        if (_r != 0)                                                                      \
+            return Status::error(PCR_CUDA_ERROR, std::string("NCCL error: ") +            \
+                                 nccl_->GetErrorString(_r) + " (" #expr ")");             \
+    } while (0)
+
+Status comm_unique_id(void* id128)
+{
+    std::string err;
+    NcclApi* api = nccl_load(err);
+    if (!api) return Status::error(PCR_CUDA_ERROR, err);
+    NcclApi::UniqueId id;
+    const int r = api->GetUniqueId(&id);
+    if (r != 0) return Status::error(PCR_CUDA_ERROR, std::string("NCCL error: ") + api->GetErrorString(r));
+    std::memcpy(id128, id.internal, 128);
+    return Status::success();
+}
+
+void engine_comm_destroy(NcclApi* api, void* comm)
+{
+    if (api && comm) api->CommDestroy(comm);
+}
+
+Status Engine::comm_init(const void* id128, int rank, int world)
+{
+    if (world < 1 || world > kMaxParts || rank < 0 || rank >= world)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: world size must be 1..8 and 0 <= rank < world");
+    if (world == 1) { rank_ = 0; world_ = 1; return Status::success(); }
+    std::string err;
+    nccl_ = nccl_load(err);
+    if (!nccl_) return Status::error(PCR_CUDA_ERROR, err);
+    CU_TRY(cudaSetDevice(device_));
+    NcclApi::UniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    NC_TRY(nccl_->CommInitRank(&comm_, world, id, rank));
+    rank_ = rank;
+    world_ = world;
+    CU_TRY(cudaMalloc(&d_touched_all_, std::max(1, n_tiles_) * sizeof(uint32_t)));
+    return Status::success();
+}
+
+Status Engine::comm_barrier()
+{
+    if (world_ == 1) return synchronize();
+    CU_TRY(cudaSetDevice(device_));
+    NC_TRY(nccl_->AllReduce(d_touched_all_, d_touched_all_, 1, NcclApi::kUint32, NcclApi::kMax, comm_, compute_));
+    CU_TRY(cudaStreamSynchronize(compute_));
+    return Status::success();
+}
+
+// Multi-GPU finalize.  Rank k owns the row slice [row0_k, row1_k).  Every rank
+// ships its partial records of slice j to rank j (NCCL send/recv = an all-to-all
+// over NVLink, same volume as a reduce-scatter but layout-agnostic: records mix
+// f32 sums with ordered-s32 max/min words, which no single ncclRedOp covers);
+// the owner merges the `world` parts in rank order inside the finalize kernel
+// (Op::merge, builtin_ops.h:15,28,41,54,67,95-97 — fixed order, so the float sums
+// do not depend on arrival order); the finalized slices are then exchanged so
+// every rank ends with complete bands.
+Status Engine::finalize_multi()
+{
+    const size_t rows_per = (static_cast<size_t>(grid_.height) + world_ - 1) / world_;
+    auto row0 = [&](int k) { return std::min(static_cast<size_t>(grid_.height), rows_per * k); };
+    auto slice_cells = [&](int k) { return (row0(k + 1) - row0(k)) * static_cast<size_t>(grid_.width); };
+    const size_t max_slice = rows_per * static_cast<size_t>(grid_.width);
+    const size_t my0 = row0(rank_) * grid_.width, my_cells = slice_cells(rank_);
+
+    NC_TRY(nccl_->AllReduce(d_touched_, d_touched_all_, std::max(1, n_tiles_), NcclApi::kUint32,
+                            NcclApi::kMax, comm_, compute_));
+
+    for (size_t i = 0; i < reductions_.size(); ++i)
+        if (reductions_[i].rejected)
+            CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), compute_));
+
+    for (Pass& p : passes_) {
+        const size_t W = p.layout.width;
+        if (!p.d_combined) CU_TRY(cudaMalloc(&p.d_combined, static_cast<size_t>(world_) * max_slice * W * 4));
+        NC_TRY(nccl_->GroupStart());
+        for (int k = 0; k < world_; ++k) {
+            if (k == rank_) continue;
+            if (slice_cells(k))
+                NC_TRY(nccl_->Send(p.d_state + row0(k) * grid_.width * W, slice_cells(k) * W, NcclApi::kUint32, k, comm_, compute_));
+            if (my_cells)
+                NC_TRY(nccl_->Recv(p.d_combined + static_cast<size_t>(k) * max_slice * W, my_cells * W, NcclApi::kUint32, k, comm_, compute_));
+        }
+        NC_TRY(nccl_->GroupEnd());
+
+        StateParts parts{};
+        parts.n = world_;
+        for (int k = 0; k < world_; ++k)
+            parts.part[k] = (k == rank_) ? p.d_state + my0 * W : p.d_combined + static_cast<size_t>(k) * max_slice * W;
+        prof_begin(PROF_FIN, compute_);
+        CU_TRY(launch_finalize(compute_, parts, my0, my0, my_cells, d_out_, cells_, gp_, p.layout, p.fin, d_touched_all_));
+        prof_end(compute_);
+    }
+
+    // all-gather of the finalized slices, band by band
+    NC_TRY(nccl_->GroupStart());
+    for (size_t b = 0; b < reductions_.size(); ++b) {
+        if (reductions_[b].rejected) continue;
+        float* band = d_out_ + b * cells_;
+        for (int k = 0; k < world_; ++k) {
+            if (k == rank_) continue;
+            if (my_cells) NC_TRY(nccl_->Send(band + my0, my_cells, NcclApi::kFloat32, k, comm_, compute_));
+            if (slice_cells(k)) NC_TRY(nccl_->Recv(band + row0(k) * grid_.width, slice_cells(k), NcclApi::kFloat32, k, comm_, compute_));
+        }
+    }
+    NC_TRY(nccl_->GroupEnd());
+    return Status::success();
+}
+
+}  // namespace pcrb

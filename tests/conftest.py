@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The plain-C restatement (oracle/pcr_oracle.c), built on demand with gcc."""
+    import oracle as orc
+    return orc.Oracle()
+
+
+@pytest.fixture(scope="session")
+def pcr():
+    from pointcloud_raster_b200 import pcr as _pcr
+    return _pcr
+
+
+@pytest.fixture(scope="session")
+def gpu_pcr(pcr):
+    """The product API, with a loud failure (not a skip) when the box has no usable GPU:
+    -m gpu tests must never pass on a fallback."""
+    assert pcr.device_count() > 0, "GPU test selected but no CUDA device is visible"
+    return pcr

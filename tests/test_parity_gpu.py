@@ -1,0 +1,349 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the public pcr API,
+i.e. through the C-ABI of libpcr_b200.so; the oracle (oracle/pcr_oracle.c) and the committed
+reference fixtures (tests/golden/) are only the checkers.  /root/reference is never read.
+
+Bars (BASELINE.json north_star):
+  * cell indices (via Count), Count, Max, Min: bit-exact;
+  * Sum / Average / WeightedAverage: within util.compare_bands' stated fp32 bound;
+  * NaN masks identical (touched-tile rule included);
+  * deterministic mode: byte-identical across runs.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+import make_golden as mg
+from known_answers import ACCUMULATOR, pipeline_cases
+from util import (boundary_cloud, clustered_cloud, compare_bands, grid_desc, make_grid, run_product,
+                  spec, uniform_cloud)
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+# Line endpoints use f64 cos/sin rounded to f32 where the reference uses glibc cosf/sinf; the two
+# differ in the last bit for a tiny fraction of angles, which can move an endpoint across a .5
+# rounding boundary.  Measured flip rate is reported by test_line_flip_rate; fixtures allow 0.
+ALL_POINT = ("Sum", "Max", "Min", "Average", "WeightedAverage", "Count")
+
+
+def to_product_spec(pcr, s):
+    p = pcr.ReductionSpec()
+    p.value_channel = s.value_channel
+    p.type = pcr.ReductionType(int(s.type))
+    p.output_band_name = s.output_band_name
+    for k, v in vars(s.glyph).items():
+        setattr(p.glyph, k, pcr.GlyphType(int(v)) if k == "type" else v)
+    return p
+
+
+def product_grid(pcr, gd):
+    gc = pcr.GridConfig()
+    gc.bounds.min_x, gc.bounds.min_y, gc.bounds.max_x, gc.bounds.max_y = gd.min_x, gd.min_y, gd.max_x, gd.max_y
+    gc.cell_size_x, gc.cell_size_y = gd.cell_size_x, gd.cell_size_y
+    gc.tile_width, gc.tile_height = gd.tile_width, gd.tile_height
+    gc.compute_dimensions()
+    return gc
+
+
+# ---- reference fixtures ---------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_reference_fixture(gpu_pcr, oracle, path):
+    gd, clouds, specs, ref_bands = mg.load(path)
+    got, _ = run_product(gpu_pcr, product_grid(gpu_pcr, gd), clouds, [to_product_spec(gpu_pcr, s) for s in specs])
+    compare_bands(oracle, gd, clouds, specs, ref_bands, got, os.path.basename(path), device_weights=True)
+
+
+@pytest.mark.parametrize("name", sorted(ACCUMULATOR))
+def test_reference_gtest_accumulator_vectors(gpu_pcr, name):
+    k = ACCUMULATOR[name]
+    gc = make_grid(gpu_pcr, k["w"], k["h"], tile=k["tile"])
+    got, _ = run_product(gpu_pcr, gc, k["clouds"], [spec(gpu_pcr, "v", gpu_pcr.ReductionType(t)) for t in k["types"]])
+    for band, exp in zip(got, k["expect_head"]):
+        np.testing.assert_array_equal(band[0], np.array(exp, np.float32))
+
+
+@pytest.mark.parametrize("name", sorted(pipeline_cases()))
+def test_reference_gtest_pipeline_vectors(gpu_pcr, name):
+    k = pipeline_cases()[name]
+    gc = make_grid(gpu_pcr, k["w"], k["h"], tile=k["tile"])
+    got, p = run_product(gpu_pcr, gc, k["clouds"],
+                         [spec(gpu_pcr, k["channel"], gpu_pcr.ReductionType(t)) for t in k["types"]])
+    for band, exp in zip(got, k["expect"]):
+        np.testing.assert_array_equal(band, exp)
+    st = p.stats()                                            # test_pipeline.cpp:398-441
+    assert st.collections_processed == len(k["clouds"])
+    assert st.points_processed == sum(len(c[0]) for c in k["clouds"])
+
+
+# ---- differential vs the oracle, Point glyph ---------------------------------------------
+def point_specs(pcr, channel="value"):
+    return [spec(pcr, channel, getattr(pcr.ReductionType, n)) for n in ALL_POINT]
+
+
+def check_vs_oracle(pcr, oracle, gc, clouds, specs, what, device_weights=False, **knobs):
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, clouds, specs)
+    got, p = run_product(pcr, gc, clouds, specs, **knobs)
+    compare_bands(oracle, gd, clouds, specs, ref, got, what, device_weights=device_weights)
+    return got, p
+
+
+@pytest.mark.parametrize("loc", ["Host", "HostPinned", "Device"])
+def test_point_uniform_all_reducers(gpu_pcr, oracle, loc):
+    gc = make_grid(gpu_pcr, 256, 192, tile=64)
+    x, y, ch = uniform_cloud(300_000, 256, 192, seed=42, margin=-3.0)   # some points outside
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], point_specs(gpu_pcr), f"uniform/{loc}",
+                    loc=getattr(gpu_pcr.MemoryLocation, loc))
+
+
+def test_point_boundary_probes(gpu_pcr, oracle):
+    for (w, h, cell, tile) in [(64, 48, 1.0, 16), (30, 20, 0.3, 7), (50, 50, 2.0, 4096), (17, 33, 1.7, 5)]:
+        gc = make_grid(gpu_pcr, w * cell, h * cell, cell=cell, tile=tile)
+        x, y, ch = boundary_cloud(w * cell, h * cell)
+        ch["value"][::53] = np.nan
+        ch["value"][3::59] = -np.inf
+        ch["value"][5::61] = np.inf
+        ch["value"][7::67] = np.float32(-3.4028235e38)
+        check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], point_specs(gpu_pcr), f"boundary {w}x{h} cs={cell}")
+
+
+def test_point_offset_bounds_negative_coords(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 37.3, 21.9, cell=0.7, tile=8, min_x=-1234.5678, min_y=987654.321, cell_y=-0.35)
+    rng = np.random.default_rng(5)
+    n = 100_000
+    x = rng.uniform(gc.bounds.min_x - 1, gc.bounds.max_x + 1, n)
+    y = rng.uniform(gc.bounds.min_y - 1, gc.bounds.max_y + 1, n)
+    ch = {"value": rng.normal(0, 100, n).astype(np.float32)}
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], point_specs(gpu_pcr), "offset bounds")
+
+
+def test_point_clustered_clipped_to_bbox(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 512, 512, tile=128)
+    x, y, ch = clustered_cloud(400_000, 512, 512, seed=42)
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], point_specs(gpu_pcr), "clustered")
+
+
+def test_point_sorted_input_exercises_run_aggregation(gpu_pcr, oracle):
+    """Scan-ordered cloud: long runs of consecutive points in one cell (warp run aggregation)."""
+    gc = make_grid(gpu_pcr, 64, 64, tile=32)
+    rng = np.random.default_rng(9)
+    n = 200_000
+    x = np.sort(rng.uniform(0, 64, n)); y = np.repeat(rng.uniform(0, 64, n // 100), 100)
+    ch = {"value": rng.uniform(-1, 1, n).astype(np.float32)}
+    ch["value"][::41] = np.nan
+    specs = [spec(gpu_pcr, "value", gpu_pcr.ReductionType.Max), spec(gpu_pcr, "value", gpu_pcr.ReductionType.Min),
+             spec(gpu_pcr, "value", gpu_pcr.ReductionType.Count)]
+    for knobs in ({}, {"warp_aggregate": 2}, {"point_kernel": 2}):
+        check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], specs, f"sorted {knobs}", **knobs)
+    ch2 = {"value": rng.uniform(0, 1, n).astype(np.float32)}
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch2)], point_specs(gpu_pcr), "sorted sums")
+
+
+@pytest.mark.parametrize("knobs", [{"point_kernel": 1}, {"point_kernel": 2}, {"point_kernel": 2, "warp_aggregate": 2},
+                                   {"ring_slot_points": 4096, "ring_depth": 2}])
+def test_point_kernel_variants_and_ring(gpu_pcr, oracle, knobs):
+    gc = make_grid(gpu_pcr, 300, 200, tile=128)
+    x, y, ch = uniform_cloud(123_457, 300, 200, seed=3, margin=-1.0)   # odd count: tails
+    for loc in ("Host", "Device"):
+        check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], point_specs(gpu_pcr), f"{knobs}/{loc}",
+                        loc=getattr(gpu_pcr.MemoryLocation, loc), **knobs)
+
+
+def test_point_multiple_ingests_and_refinalize(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 128, 128, tile=32)
+    clouds = [uniform_cloud(50_000, 128, 40, seed=s) for s in (1, 2, 3)]     # only the south rows
+    specs = point_specs(gpu_pcr)
+    gd = grid_desc(gc)
+    cfg = gpu_pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = specs; cfg.exec_mode = gpu_pcr.ExecutionMode.GPU
+    p = gpu_pcr.Pipeline.create(cfg)
+    from util import cloud as mk
+    for i, c in enumerate(clouds):
+        p.ingest(mk(gpu_pcr, *c))
+        p.finalize()                                # finalize after every ingest, like the benchmarks do
+        got = [np.array(p.result().band_array(b)) for b in range(len(specs))]
+        ref = oracle.run(gd, clouds[:i + 1], specs)
+        compare_bands(oracle, gd, clouds[:i + 1], specs, ref, got, f"after ingest {i}")
+    assert np.isnan(got[0][:64]).all()              # untouched north tiles stay NaN, even for Sum
+
+
+def test_fused_multi_channel_and_many_reductions(gpu_pcr, oracle):
+    """More reductions than one record can hold: the planner must split passes."""
+    gc = make_grid(gpu_pcr, 96, 96, tile=32)
+    rng = np.random.default_rng(17)
+    n = 80_000
+    x, y = rng.uniform(0, 96, n), rng.uniform(0, 96, n)
+    ch = {k: rng.normal(i, 2, n).astype(np.float32) for i, k in enumerate("abcdef")}
+    R = gpu_pcr.ReductionType
+    specs = [spec(gpu_pcr, k, t) for k in "abcdef" for t in (R.Sum, R.Max, R.Min, R.Average)] + \
+            [spec(gpu_pcr, "a", R.Count)]
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], specs, "25 reductions / 6 channels")
+
+
+def test_empty_and_all_outside_clouds(gpu_pcr):
+    gc = make_grid(gpu_pcr, 16, 16)
+    specs = point_specs(gpu_pcr)
+    got, p = run_product(gpu_pcr, gc, [(np.array([]), np.array([]), {"value": np.array([], np.float32)})], specs)
+    assert all(np.isnan(b).all() for b in got)
+    assert p.stats().collections_processed == 0       # empty cloud is a no-op (pipeline.cpp:284-287)
+    got, p = run_product(gpu_pcr, gc, [(np.array([-5.0, 99.0]), np.array([3.0, 3.0]),
+                                        {"value": np.array([1, 2], np.float32)})], specs)
+    assert all(np.isnan(b).all() for b in got)         # no tile touched -> NaN everywhere
+    assert p.stats().points_processed == 2             # but the points count (pipeline.cpp:749)
+
+
+# ---- glyphs vs the oracle ---------------------------------------------------------------------
+def test_line_vs_oracle(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 200, 160, tile=64)
+    x, y, ch = uniform_cloud(60_000, 200, 160, seed=8, margin=-1.0)
+    rng = np.random.default_rng(8)
+    ch["hl"] = rng.uniform(0, 20, len(x)).astype(np.float32)
+    specs = []
+    for t in ("WeightedAverage", "Sum", "Count", "Average"):
+        s = gpu_pcr.line_splat_spec("value", "direction", "hl", max_radius_cells=18.0)
+        s.type = getattr(gpu_pcr.ReductionType, t)
+        specs.append(s)
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], specs, "line", device_weights=True)
+
+
+def test_line_flip_rate(gpu_pcr, oracle):
+    """Cell-set parity of the Line glyph at scale: count the cells whose Count differs from the
+    oracle's (device f64 cos/sin vs glibc cosf/sinf).  Stated bound: <= 1e-6 of painted cells."""
+    gc = make_grid(gpu_pcr, 1000, 1000)
+    x, y, ch = uniform_cloud(1_000_000, 1000, 1000, seed=42)
+    ch["hl"] = np.full(len(x), 16.0, np.float32)
+    s = gpu_pcr.line_splat_spec("value", "direction", "hl", max_radius_cells=18.0)
+    s.type = gpu_pcr.ReductionType.Count
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, [(x, y, ch)], [s])[0]
+    got, _ = run_product(gpu_pcr, gc, [(x, y, ch)], [s])
+    painted = float(np.nansum(ref))
+    flips = float(np.nansum(np.abs(np.nan_to_num(got[0]) - np.nan_to_num(ref))))
+    print(f"line flip rate: {flips:.0f} cell-visits differ of {painted:.0f} painted ({flips / painted:.2e})")
+    assert flips <= max(2.0, 1e-6 * painted)
+
+
+def test_gaussian_vs_oracle(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 160, 120, tile=64)
+    rng = np.random.default_rng(21)
+    n = 6000
+    x, y = rng.uniform(-1, 161, n), rng.uniform(-1, 121, n)
+    ch = {"value": rng.uniform(0, 1, n).astype(np.float32), "sigma": rng.uniform(-0.5, 5, n).astype(np.float32),
+          "s2": rng.uniform(0.3, 3, n).astype(np.float32), "rot": rng.uniform(-3.2, 3.2, n).astype(np.float32)}
+    specs = []
+    for t in ("WeightedAverage", "Sum", "Count"):
+        s = gpu_pcr.gaussian_splat_spec("value", "sigma", "sigma", default_sigma=1.5, max_radius_cells=12.0)
+        s.type = getattr(gpu_pcr.ReductionType, t)
+        specs.append(s)
+    specs.append(gpu_pcr.gaussian_splat_spec("value", "sigma", "s2", "rot", default_sigma=2.0, max_radius_cells=10.0))
+    specs.append(gpu_pcr.gaussian_splat_spec("value", default_sigma_x=16.0, default_sigma_y=16.0, max_radius_cells=32.0))
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], specs, "gaussian", device_weights=True)
+
+
+def test_glyph_with_max_is_not_implemented(gpu_pcr):
+    gc = make_grid(gpu_pcr, 16, 16)
+    s = gpu_pcr.line_splat_spec("value")
+    s.type = gpu_pcr.ReductionType.Max
+    cfg = gpu_pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = [s]; cfg.exec_mode = gpu_pcr.ExecutionMode.GPU
+    p = gpu_pcr.Pipeline.create(cfg)
+    assert p is not None
+    from util import cloud as mk
+    with pytest.raises(RuntimeError, match="glyph splatting only supports"):
+        p.ingest(mk(gpu_pcr, [1.0], [1.0], {"value": [1.0]}))
+
+
+# ---- API behaviour ---------------------------------------------------------------------------
+def test_error_behaviour(gpu_pcr):
+    from util import cloud as mk
+    gc = make_grid(gpu_pcr, 8, 8)
+    cfg = gpu_pcr.PipelineConfig(); cfg.grid = gc; cfg.exec_mode = gpu_pcr.ExecutionMode.GPU
+    p = gpu_pcr.Pipeline.create(cfg)                        # no reductions: create ok, validate fails
+    assert p is not None
+    with pytest.raises(RuntimeError, match="at least one reduction"):
+        p.validate()
+    cfg.reductions = [spec(gpu_pcr, "intensity", gpu_pcr.ReductionType.Sum)]
+    p = gpu_pcr.Pipeline.create(cfg)
+    p.validate()
+    with pytest.raises(RuntimeError, match="value channel not found: intensity"):
+        p.ingest(mk(gpu_pcr, [1.0], [1.0], {"other": [1.0]}))
+    c = gpu_pcr.PointCloud.create(4)
+    c.set_x_array(np.ones(4)); c.set_y_array(np.ones(4)); c.add_channel("intensity", gpu_pcr.DataType.Int32)
+    with pytest.raises(RuntimeError, match="must be Float32"):
+        p.ingest(c)
+    cfg.reductions = [spec(gpu_pcr, "intensity", gpu_pcr.ReductionType.Median)]
+    assert gpu_pcr.Pipeline.create(cfg) is None             # unregistered op: create fails (nullptr upstream)
+    cfg.reductions = [spec(gpu_pcr, "intensity", gpu_pcr.ReductionType.Sum)]
+    cfg.exec_mode = gpu_pcr.ExecutionMode.CPU
+    assert gpu_pcr.Pipeline.create(cfg) is None             # no CPU path behind this API
+    for mode in ("Auto", "Hybrid"):                         # both are the GPU path
+        cfg.exec_mode = getattr(gpu_pcr.ExecutionMode, mode)
+        assert gpu_pcr.Pipeline.create(cfg) is not None
+
+
+def test_progress_callback_and_cancel(gpu_pcr):
+    from util import cloud as mk
+    gc = make_grid(gpu_pcr, 8, 8)
+    cfg = gpu_pcr.PipelineConfig(); cfg.grid = gc; cfg.exec_mode = gpu_pcr.ExecutionMode.GPU
+    cfg.reductions = [spec(gpu_pcr, "v", gpu_pcr.ReductionType.Count)]
+    p = gpu_pcr.Pipeline.create(cfg)
+    seen = []
+    p.set_progress_callback(lambda info: (seen.append((info.collections_processed, info.points_processed)), True)[1])
+    c = mk(gpu_pcr, [1.0, 2.0], [1.0, 2.0], {"v": [1.0, 1.0]})
+    p.ingest(c); p.ingest(c)
+    assert seen == [(1, 2), (2, 4)]
+    p.set_progress_callback(lambda info: False)
+    with pytest.raises(RuntimeError, match="cancelled by user"):
+        p.ingest(c)
+
+
+def test_band_names_and_result_grid(gpu_pcr):
+    gc = make_grid(gpu_pcr, 8, 6)
+    specs = [spec(gpu_pcr, "v", gpu_pcr.ReductionType.Average), spec(gpu_pcr, "v", gpu_pcr.ReductionType.Max, "peak")]
+    got, p = run_product(gpu_pcr, gc, [([1.5], [1.5], {"v": [2.0]})], specs)
+    g = p.result()
+    assert (g.cols(), g.rows(), g.num_bands()) == (8, 6, 2)
+    assert g.band_desc(0).name == "v_3" and g.band_desc(1).name == "peak"   # pipeline.cpp:1178-1180
+    assert g.band_array(0).shape == (6, 8) and g.band_array(0).dtype == np.float32
+    assert got[0][4, 1] == 2.0 and got[1][4, 1] == 2.0
+
+
+# ---- deterministic mode -----------------------------------------------------------------------
+def test_deterministic_mode_bit_reproducible(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 128, 128, tile=64)
+    x, y, ch = clustered_cloud(300_000, 128, 128, seed=4)
+    specs = point_specs(gpu_pcr)
+    runs = []
+    for _ in range(3):
+        got, _ = run_product(gpu_pcr, gc, [(x, y, ch), (x[::3], y[::3], {"value": ch["value"][::3]})], specs,
+                             deterministic=True)
+        runs.append([b.tobytes() for b in got])
+    assert runs[0] == runs[1] == runs[2]
+    clouds = [(x, y, ch), (x[::3], y[::3], {"value": ch["value"][::3]})]
+    gd = grid_desc(gc)
+    compare_bands(oracle, gd, clouds, specs, oracle.run(gd, clouds, specs),
+                  [np.frombuffer(b, np.float32).reshape(128, 128) for b in runs[0]], "deterministic")
+    # in deterministic mode the fold is the oracle's: original point order per cell -> Sum bit-exact
+    ref = oracle.run(gd, [clouds[0]], [specs[0]])[0]
+    got, _ = run_product(gpu_pcr, gc, [clouds[0]], [specs[0]], deterministic=True)
+    assert np.array_equal(got[0], ref, equal_nan=True)
+
+
+# ---- full-size properties (BASELINE config 2: 5M points, 1000x1000) ------------------------------
+def test_full_size_point_config(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 1000, 1000)
+    x, y, ch = uniform_cloud(5_000_000, 1000, 1000, seed=42)
+    R = gpu_pcr.ReductionType
+    specs = [spec(gpu_pcr, "value", R.Sum), spec(gpu_pcr, "value", R.Count), spec(gpu_pcr, "value", R.Max)]
+    got, p = run_product(gpu_pcr, gc, [(x, y, ch)], specs)
+    assert np.nansum(got[1].astype(np.float64)) == 5_000_000            # every point counted exactly once
+    assert abs(np.nansum(got[0].astype(np.float64)) - ch["value"].astype(np.float64).sum()) < 1.0
+    assert np.nanmax(got[2]) == ch["value"].max()
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, [(x, y, ch)], specs)                             # the C oracle does 5M in < 1 s
+    compare_bands(oracle, gd, [(x, y, ch)], specs, ref, got, "config 2 full size")
+    # idempotence of finalize, exact doubling of Count on a second ingest
+    from util import cloud as mk
+    p.ingest(mk(gpu_pcr, x, y, ch)); p.finalize()
+    assert np.array_equal(np.array(p.result().band_array(1)), 2 * ref[1], equal_nan=True)
