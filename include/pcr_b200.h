@@ -131,6 +131,7 @@ typedef struct pcr_profile {
     double   init_ms;           uint64_t init_launches;        /* state identity fill */
     uint64_t h2d_bytes;         uint64_t d2h_bytes;            /* bytes moved by ingest ring / finalize */
     uint64_t points;                                           /* points fed to accumulate kernels */
+    uint64_t kernel_launches;                                  /* every kernel of this library launched */
 } pcr_profile;
 
 typedef struct pcr_pipeline pcr_pipeline;
@@ -173,7 +174,8 @@ int pcr_pipeline_ingest(pcr_pipeline *p, const double *x, const double *y, size_
  * Finalizes on the device and copies every band to host memory owned by the
  * pipeline.  May be called repeatedly; later ingests keep accumulating. */
 int pcr_pipeline_finalize(pcr_pipeline *p);
-/* Same, but leaves the finalized bands in HBM only (no D2H). */
+/* Same, but leaves the finalized bands in HBM only (no D2H).  With async_ingest = 1 it
+ * returns without synchronizing (stream-ordered); call pcr_pipeline_synchronize. */
 int pcr_pipeline_finalize_device(pcr_pipeline *p);
 /* Pipeline::result()->band_f32(i), include/pcr/core/grid.h:62-66: row-major
  * rows x cols float32, valid until the next finalize/destroy. */
@@ -195,6 +197,11 @@ int pcr_pipeline_reset(pcr_pipeline *p);
 int pcr_pipeline_synchronize(pcr_pipeline *p);
 
 /* ---- profiling (new; feeds bench.py's roofline block) ---------------------- */
+/* Device-side stopwatch: begin records a CUDA event on the pipeline's compute stream
+ * (the stream every kernel, the finalize D2H and the waits on the copy stream are
+ * ordered on); end records a second one, synchronizes and returns the elapsed ms. */
+int pcr_pipeline_timer_begin(pcr_pipeline *p);
+int pcr_pipeline_timer_end(pcr_pipeline *p, double *elapsed_ms);
 int pcr_pipeline_profile_enable(pcr_pipeline *p, int32_t on);
 int pcr_pipeline_profile_reset(pcr_pipeline *p);
 int pcr_pipeline_profile_read(pcr_pipeline *p, pcr_profile *out);

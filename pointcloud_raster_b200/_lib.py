@@ -65,7 +65,8 @@ class Profile(C.Structure):
                 ("sort_ms", C.c_double), ("sort_launches", C.c_uint64),
                 ("finalize_ms", C.c_double), ("finalize_launches", C.c_uint64),
                 ("init_ms", C.c_double), ("init_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("points", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("points", C.c_uint64),
+                ("kernel_launches", C.c_uint64)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.POINTER(Progress), C.c_void_p)
@@ -102,6 +103,8 @@ SYMBOLS = [
     ("pcr_pipeline_profile_enable", C.c_int, [C.c_void_p, C.c_int32]),
     ("pcr_pipeline_profile_reset", C.c_int, [C.c_void_p]),
     ("pcr_pipeline_profile_read", C.c_int, [C.c_void_p, C.POINTER(Profile)]),
+    ("pcr_pipeline_timer_begin", C.c_int, [C.c_void_p]),
+    ("pcr_pipeline_timer_end", C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     ("pcr_comm_unique_id", C.c_int, [C.c_void_p]),
     ("pcr_pipeline_comm_init", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     ("pcr_pipeline_comm_barrier", C.c_int, [C.c_void_p]),

@@ -221,6 +221,14 @@ int pcr_pipeline_profile_read(pcr_pipeline* p, pcr_profile* out)
     return finish(eng(p)->profile_read(*out));
 }
 
+int pcr_pipeline_timer_begin(pcr_pipeline* p) { NEED(p); return finish(eng(p)->timer_begin()); }
+int pcr_pipeline_timer_end(pcr_pipeline* p, double* elapsed_ms)
+{
+    NEED(p);
+    if (!elapsed_ms) return fail(PCR_INVALID_ARGUMENT, "null output pointer");
+    return finish(eng(p)->timer_end(*elapsed_ms));
+}
+
 int pcr_comm_unique_id(void* id128)
 {
     if (!id128) return fail(PCR_INVALID_ARGUMENT, "null id buffer");

@@ -369,7 +369,7 @@ Status Engine::alloc_state()
 Status Engine::init_state()
 {
     prof_begin(PROF_INIT, compute_);
-    for (Pass& p : passes_) CU_TRY(launch_init_state(compute_, p.d_state, cells_, p.layout));
+    for (Pass& p : passes_) { CU_TRY(launch_init_state(compute_, p.d_state, cells_, p.layout)); ++launches_; }
     CU_TRY(cudaMemsetAsync(d_touched_, 0, std::max(1, n_tiles_) * sizeof(uint32_t), compute_));
     prof_end(compute_);
     return Status::success();
@@ -416,6 +416,7 @@ Engine::~Engine()
     cudaFree(d_sort_tmp_); cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_idx_); cudaFree(d_idx_alt_);
     for (auto& sp : prof_open_) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& ev : prof_free_) cudaEventDestroy(ev);
+    if (timer_a_) { cudaEventDestroy(timer_a_); cudaEventDestroy(timer_b_); }
     delete pool_;
     if (compute_) cudaStreamDestroy(compute_);
     if (copy_) cudaStreamDestroy(copy_);
@@ -484,7 +485,7 @@ Status Engine::profile_reset()
     CU_TRY(cudaSetDevice(device_));
     ST_TRY(prof_collect());
     for (int k = 0; k < PROF_KINDS; ++k) { prof_ms_[k] = 0; prof_n_[k] = 0; }
-    prof_h2d_ = prof_d2h_ = prof_points_ = 0;
+    prof_h2d_ = prof_d2h_ = prof_points_ = launches_ = 0;
     return Status::success();
 }
 
@@ -497,6 +498,28 @@ Status Engine::profile_read(pcr_profile& o)
     o.finalize_ms = prof_ms_[PROF_FIN];    o.finalize_launches = prof_n_[PROF_FIN];
     o.init_ms = prof_ms_[PROF_INIT];       o.init_launches = prof_n_[PROF_INIT];
     o.h2d_bytes = prof_h2d_; o.d2h_bytes = prof_d2h_; o.points = prof_points_;
+    o.kernel_launches = launches_;
+    return Status::success();
+}
+
+Status Engine::timer_begin()
+{
+    CU_TRY(cudaSetDevice(device_));
+    if (!timer_a_) { CU_TRY(cudaEventCreate(&timer_a_)); CU_TRY(cudaEventCreate(&timer_b_)); }
+    CU_TRY(cudaEventRecord(timer_a_, compute_));
+    return Status::success();
+}
+
+Status Engine::timer_end(double& ms)
+{
+    CU_TRY(cudaSetDevice(device_));
+    if (!timer_a_) return Status::error(PCR_INVALID_ARGUMENT, "pipeline: timer_end without timer_begin");
+    CU_TRY(cudaStreamSynchronize(copy_));
+    CU_TRY(cudaEventRecord(timer_b_, compute_));
+    CU_TRY(cudaEventSynchronize(timer_b_));
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, timer_a_, timer_b_));
+    ms = f;
     return Status::success();
 }
 
@@ -571,6 +594,7 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
         if (p.glyph.type == PCR_GLYPH_POINT) {
             CU_TRY(launch_point_accumulate(compute_, point_variant_, warp_aggregate_, dx, dy, ch, n,
                                            p.d_state, gp_, p.layout, d_touched_, sm_count_));
+            ++launches_;
         } else {
             GlyphParams g{};
             auto opt = [&](const std::string& name) -> const float* {
@@ -587,6 +611,7 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
                 CU_TRY(launch_line_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
             else
                 CU_TRY(launch_gaussian_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
+            ++launches_;
         }
     }
     prof_end(compute_);
@@ -697,7 +722,7 @@ Status Engine::finalize(bool to_host)
         CU_TRY(cudaMemcpyAsync(h_out_, d_out_, bytes, cudaMemcpyDeviceToHost, compute_));
         prof_d2h_ += bytes;
     }
-    CU_TRY(cudaStreamSynchronize(compute_));
+    if (to_host || !async_device_ingest_) CU_TRY(cudaStreamSynchronize(compute_));
     finalized_ = true;
     return Status::success();
 }
@@ -713,6 +738,7 @@ Status Engine::finalize_single()
         parts.part[0] = p.d_state;
         parts.n = 1;
         CU_TRY(launch_finalize(compute_, parts, 0, 0, cells_, d_out_, cells_, gp_, p.layout, p.fin, d_touched_));
+        ++launches_;
     }
     prof_end(compute_);
     return Status::success();

@@ -99,6 +99,8 @@ public:
     Status profile_enable(bool on);
     Status profile_reset();
     Status profile_read(pcr_profile& out);
+    Status timer_begin();
+    Status timer_end(double& ms);
 
     Status comm_init(const void* id128, int rank, int world);
     Status comm_barrier();
@@ -185,7 +187,8 @@ private:
     ProfSpan prof_cur_{};
     double prof_ms_[PROF_KINDS] = {0, 0, 0, 0};
     uint64_t prof_n_[PROF_KINDS] = {0, 0, 0, 0};
-    uint64_t prof_h2d_ = 0, prof_d2h_ = 0, prof_points_ = 0;
+    uint64_t prof_h2d_ = 0, prof_d2h_ = 0, prof_points_ = 0, launches_ = 0;
+    cudaEvent_t timer_a_ = nullptr, timer_b_ = nullptr;
 
     // ---- multi-GPU ----
     NcclApi* nccl_ = nullptr;

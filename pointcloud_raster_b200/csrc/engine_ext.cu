@@ -62,12 +62,14 @@ Status Engine::run_passes_deterministic(const double* dx, const double* dy, size
         CU_TRY(det_sort(compute_, d_sort_tmp_, sort_tmp_bytes_, d_keys_, d_keys_alt_, d_idx_, d_idx_alt_,
                         cnt, key_bits));
         prof_end(compute_);
+        launches_ += 2;   // key build + radix sort (CUB launches several kernels; counted as one)
         prof_begin(PROF_ACC, compute_);
         for (Pass& p : passes_) {
             ChannelPtrs ch{};
             for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])] + p0;
             CU_TRY(det_point_reduce(compute_, d_keys_, d_idx_, cnt, ch, p.d_state, p.layout,
                                     static_cast<uint32_t>(cells_)));
+            ++launches_;
         }
         prof_end(compute_);
         prof_points_ += cnt;
@@ -220,6 +222,7 @@ Status Engine::finalize_multi()
             parts.part[k] = (k == rank_) ? p.d_state + my0 * W : p.d_combined + static_cast<size_t>(k) * max_slice * W;
         prof_begin(PROF_FIN, compute_);
         CU_TRY(launch_finalize(compute_, parts, my0, my0, my_cells, d_out_, cells_, gp_, p.layout, p.fin, d_touched_all_));
+        ++launches_;
         prof_end(compute_);
     }
 

@@ -788,6 +788,25 @@ class Pipeline:
     def validate(self):
         check(lib.pcr_pipeline_validate(self._h))
 
+    def prepare(self, cloud):
+        """New: pre-marshal a cloud's C-ABI arguments once, for hot loops that ingest the same
+        buffers repeatedly (bench.py); returns an opaque token for ingest_prepared()."""
+        names = cloud.channel_names()
+        views = (_lib.ChannelView * max(len(names), 1))()
+        keep = [cloud]
+        for i, name in enumerate(names):
+            desc, storage = cloud._channels[name]
+            nb = _b(name)
+            keep.append(nb)
+            views[i].name = nb
+            views[i].data = PointCloud._ptr(storage)
+            views[i].dtype = int(desc.dtype)
+        return (C.c_void_p(PointCloud._ptr(cloud._x)), C.c_void_p(PointCloud._ptr(cloud._y)),
+                C.c_size_t(cloud.count()), views, C.c_int32(len(names)), C.c_int32(int(cloud.location())), keep)
+
+    def ingest_prepared(self, tok):
+        check(lib.pcr_pipeline_ingest(self._h, tok[0], tok[1], tok[2], tok[3], tok[4], tok[5]))
+
     def ingest(self, cloud):
         names = cloud.channel_names()
         views = (_lib.ChannelView * max(len(names), 1))()
@@ -810,6 +829,7 @@ class Pipeline:
             check(lib.pcr_pipeline_result_band(self._h, i, C.byref(p), C.byref(rows), C.byref(cols)))
             nbytes = rows.value * cols.value * 4
             buf = (C.c_char * nbytes).from_address(p.value)
+            buf._pcr_owner = self      # array -> buffer -> pipeline: the pinned memory outlives views
             arrays.append(np.frombuffer(buf, np.float32).reshape(rows.value, cols.value))
             name = C.create_string_buffer(512)
             check(lib.pcr_pipeline_band_name(self._h, i, name, 512))
@@ -880,6 +900,14 @@ class Pipeline:
         p = _lib.Profile()
         check(lib.pcr_pipeline_profile_read(self._h, C.byref(p)))
         return {f: getattr(p, f) for f, _ in _lib.Profile._fields_}
+
+    def timer_begin(self):
+        check(lib.pcr_pipeline_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double(0.0)
+        check(lib.pcr_pipeline_timer_end(self._h, C.byref(ms)))
+        return ms.value
 
     def comm_init(self, unique_id: bytes, rank: int, world_size: int):
         buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id else None
