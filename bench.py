@@ -144,8 +144,8 @@ def build_pipeline(pcr, device, async_ingest, rank=0, world=1, unique_id=None):
     return p, gc, specs
 
 
-def make_cloud(pcr, x, y, v, loc):
-    c = pcr.PointCloud(len(x), loc) if loc != pcr.MemoryLocation.Host else pcr.PointCloud.create(len(x))
+def make_cloud(pcr, x, y, v, loc, device=0):
+    c = pcr.PointCloud.create(len(x), loc, device)
     c.set_x_array(x)
     c.set_y_array(y)
     c.add_channel("value", pcr.DataType.Float32)
@@ -158,18 +158,24 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    unique_id = None
     from pointcloud_raster_b200 import pcr
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def new_comm_id():
+        """A fresh 128-byte NCCL id per pipeline (one communicator each), made on rank 0 and
+        broadcast — torch.distributed is only the side channel, the data path is the library's."""
+        if dist is None:
+            return None
+        import torch
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.frombuffer(bytearray(pcr.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(idt, 0)
-        unique_id = bytes(idt.cpu().numpy().tobytes())
+        return bytes(idt.cpu().numpy().tobytes())
 
     def barrier():
         if dist is not None:
@@ -187,14 +193,14 @@ def run_ours(args):
 
     K, W = args.steps, args.warmup
     # ---------------- device-resident leg (value, roofline) ----------------
-    p, gc, specs = build_pipeline(pcr, local, True, rank, world, unique_id)
+    p, gc, specs = build_pipeline(pcr, local, True, rank, world, new_comm_id())
     clouds = []
     host_sets = []
     for r in range(N_ROTATE):
         x, y, v = make_arrays(42 + 1000 * rank + r)
         if r == 0:
             host_sets.append((x, y, v))
-        clouds.append(make_cloud(pcr, x, y, v, pcr.MemoryLocation.Device))
+        clouds.append(make_cloud(pcr, x, y, v, pcr.MemoryLocation.Device, local))
     toks = [p.prepare(c) for c in clouds]
 
     def step(i):
@@ -221,9 +227,9 @@ def run_ours(args):
 
     # keep the sampler alive through the e2e leg too so that it sees >= a few samples under load
     # ---------------- end-to-end leg (host buffers through the public API) ----------------
-    pe, _, _ = build_pipeline(pcr, local, False, rank, world, unique_id)
+    pe, _, _ = build_pipeline(pcr, local, False, rank, world, new_comm_id())
     x, y, v = host_sets[0]
-    pinned = make_cloud(pcr, x, y, v, pcr.MemoryLocation.HostPinned)
+    pinned = make_cloud(pcr, x, y, v, pcr.MemoryLocation.HostPinned, local)
     pageable = make_cloud(pcr, x, y, v, pcr.MemoryLocation.Host)
     ke = max(3, min(K, 20))
 
@@ -245,6 +251,10 @@ def run_ours(args):
     e2e_pageable_ms = e2e_run(pageable, ke)
     clocks = sampler.stop() if sampler else None
 
+    if dist is not None:
+        barrier()
+        del p, pe
+        dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -407,6 +417,9 @@ def run_reference(args):
 
 
 def main():
+    if os.environ.get("PCR_BENCH_DEBUG"):        # where is a hung rank? dump all Python stacks and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PCR_BENCH_DEBUG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

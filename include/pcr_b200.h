@@ -196,6 +196,20 @@ int pcr_pipeline_reset(pcr_pipeline *p);
 /* Block until all device work of this pipeline is complete. */
 int pcr_pipeline_synchronize(pcr_pipeline *p);
 
+/* ---- GeoTIFF out (GDAL-free; host only) --------------------------------------- */
+/* write_geotiff, src/io/grid_io.cpp:39-182 (called by Pipeline::finalize when output_path is set,
+ * src/engine/pipeline.cpp:1350-1361): Float32 tiled (Big)TIFF, one plane per band, nodata NaN, band
+ * descriptions, geotransform of GridConfig::gdal_geotransform, EPSG GeoKeys.  compress: "NONE" or
+ * "DEFLATE".  bands[b] = rows*cols row-major floats (host). */
+int pcr_geotiff_write(const char *path, const float *const *bands, int32_t num_bands,
+                      const pcr_grid_desc *grid, const char *const *band_names, int32_t epsg,
+                      const char *compress, int32_t compress_level, int32_t tile_width,
+                      int32_t tile_height, int32_t bigtiff);
+/* read_geotiff_info, src/io/grid_io.cpp:395-445; bounds = {min_x, min_y, max_x, max_y} */
+int pcr_geotiff_read_info(const char *path, int32_t *width, int32_t *height, int32_t *num_bands,
+                          int32_t *epsg, double bounds[4]);
+const char *pcr_geotiff_last_error(void);
+
 /* ---- profiling (new; feeds bench.py's roofline block) ---------------------- */
 /* Device-side stopwatch: begin records a CUDA event on the pipeline's compute stream
  * (the stream every kernel, the finalize D2H and the waits on the copy stream are
@@ -215,6 +229,8 @@ int pcr_pipeline_profile_read(pcr_pipeline *p, pcr_profile *out);
  * pcr_comm_unique_id: rank 0 fills 128 bytes (ncclUniqueId) and ships them to the
  * other ranks by any side channel (bench.py uses torch.distributed). */
 int pcr_comm_unique_id(void *id128);
+/* Row slice [row0, row1) of the grid that `rank` owns (merges and finalizes) at an N-rank finalize. */
+int pcr_comm_slice_rows(int32_t height, int32_t world_size, int32_t rank, int32_t *row0, int32_t *row1);
 int pcr_pipeline_comm_init(pcr_pipeline *p, const void *id128, int32_t rank, int32_t world_size);
 int pcr_pipeline_comm_barrier(pcr_pipeline *p);
 

@@ -100,12 +100,19 @@ SYMBOLS = [
     ("pcr_pipeline_set_progress_callback", C.c_int, [C.c_void_p, PROGRESS_FN, C.c_void_p]),
     ("pcr_pipeline_reset", C.c_int, [C.c_void_p]),
     ("pcr_pipeline_synchronize", C.c_int, [C.c_void_p]),
+    ("pcr_geotiff_write", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(GridDesc),
+                                    C.POINTER(C.c_char_p), C.c_int32, C.c_char_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32]),
+    ("pcr_geotiff_read_info", C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    ("pcr_geotiff_last_error", C.c_char_p, []),
     ("pcr_pipeline_profile_enable", C.c_int, [C.c_void_p, C.c_int32]),
     ("pcr_pipeline_profile_reset", C.c_int, [C.c_void_p]),
     ("pcr_pipeline_profile_read", C.c_int, [C.c_void_p, C.POINTER(Profile)]),
     ("pcr_pipeline_timer_begin", C.c_int, [C.c_void_p]),
     ("pcr_pipeline_timer_end", C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     ("pcr_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("pcr_comm_slice_rows", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("pcr_pipeline_comm_init", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     ("pcr_pipeline_comm_barrier", C.c_int, [C.c_void_p]),
 ]

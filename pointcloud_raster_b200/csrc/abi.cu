@@ -235,6 +235,14 @@ int pcr_comm_unique_id(void* id128)
     return finish(pcrb::comm_unique_id(id128));
 }
 
+int pcr_comm_slice_rows(int32_t height, int32_t world_size, int32_t rank, int32_t* row0, int32_t* row1)
+{
+    if (!row0 || !row1 || world_size < 1 || rank < 0 || rank >= world_size || height < 0)
+        return fail(PCR_INVALID_ARGUMENT, "pcr_comm_slice_rows: bad arguments");
+    pcrb::slice_rows(height, world_size, rank, *row0, *row1);
+    return PCR_OK;
+}
+
 int pcr_pipeline_comm_init(pcr_pipeline* p, const void* id128, int32_t rank, int32_t world_size)
 {
     NEED(p);

@@ -562,6 +562,21 @@ Status Engine::ingest(const double* x, const double* y, size_t n, const pcr_chan
         if (v && v->data && v->dtype == PCR_F32) ptrs[i] = static_cast<const float*>(v->data);
     }
 
+    if (location == PCR_MEM_DEVICE) {
+        // a cloud on another GPU would fault inside the kernels: refuse it here
+        auto on_my_device = [&](const void* p) {
+            cudaPointerAttributes a{};
+            return cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice &&
+                   a.device == device_;
+        };
+        bool ok = on_my_device(x) && on_my_device(y);
+        for (const float* p : ptrs) ok = ok && (!p || on_my_device(p));
+        if (!ok) {
+            cudaGetLastError();
+            return Status::error(PCR_INVALID_ARGUMENT,
+                                 "pipeline: Device cloud does not live on cuda_device_id " + std::to_string(device_));
+        }
+    }
     Status s;
     if (location == PCR_MEM_DEVICE) s = ingest_device(x, y, n, ptrs);
     else if (location == PCR_MEM_HOST || location == PCR_MEM_HOST_PINNED)

@@ -8,6 +8,7 @@
 // run on the compute stream (the replacement for to_device_async + Hybrid mode).
 #pragma once
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -206,6 +207,13 @@ cudaError_t det_point_reduce(cudaStream_t s, const uint32_t* keys, const uint32_
                              const ChannelPtrs& ch, uint32_t* state, const PassLayout& L,
                              uint32_t invalid_key);
 Status comm_unique_id(void* id128);
+// rows [row0,row1) owned by `rank`: ceil(height/world) rows each, the last slices may be short or empty
+inline void slice_rows(int height, int world, int rank, int& row0, int& row1)
+{
+    const long per = (static_cast<long>(height) + world - 1) / world;
+    row0 = static_cast<int>(std::min<long>(height, per * rank));
+    row1 = static_cast<int>(std::min<long>(height, per * (rank + 1)));
+}
 void engine_comm_destroy(NcclApi* api, void* comm);
 
 }  // namespace pcrb

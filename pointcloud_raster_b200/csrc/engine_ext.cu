@@ -191,7 +191,8 @@ Status Engine::comm_barrier()
 Status Engine::finalize_multi()
 {
     const size_t rows_per = (static_cast<size_t>(grid_.height) + world_ - 1) / world_;
-    auto row0 = [&](int k) { return std::min(static_cast<size_t>(grid_.height), rows_per * k); };
+    auto row0 = [&](int k) -> size_t { int a, b; slice_rows(grid_.height, world_, std::min(k, world_ - 1), a, b);
+                                       return static_cast<size_t>(k >= world_ ? b : a); };
     auto slice_cells = [&](int k) { return (row0(k + 1) - row0(k)) * static_cast<size_t>(grid_.width); };
     const size_t max_slice = rows_per * static_cast<size_t>(grid_.width);
     const size_t my0 = row0(rank_) * grid_.width, my_cells = slice_cells(rank_);

@@ -1,0 +1,321 @@
+// geotiff.cu — GDAL-free GeoTIFF writer / header reader (host-only C++).
+//
+// Stands in for write_geotiff / read_geotiff_info of the reference
+// (src/io/grid_io.cpp:39-182,395-445), which are thin GDAL wrappers: Float32,
+// one sample per band, tiled (default 256x256), BigTIFF by default, nodata = NaN,
+// band descriptions, geotransform from GridConfig::gdal_geotransform
+// (src/core/grid_config.cpp:93-110), CRS from the EPSG code when known.
+// Layout written here: little-endian (Big)TIFF, PlanarConfiguration = 2 (one plane
+// per band, matching the band-major result memory), compression NONE or DEFLATE
+// (zlib, tag value 8).  GeoTIFF keys: ModelPixelScale + ModelTiepoint (north-up) or
+// ModelTransformation (cell_size_y > 0), GeoKeyDirectory with raster type
+// PixelIsArea and the projected / geographic EPSG code; GDAL_NODATA ("nan") and
+// GDAL_METADATA (band descriptions) so GDAL-based readers see what the reference
+// writes.  Not written: overviews (cloud_optimized only selects DEFLATE + tiling),
+// LZW / ZSTD (rejected with NotImplemented).
+#include "../../include/pcr_b200.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace pcrb {
+extern thread_local std::string g_geotiff_error;
+thread_local std::string g_geotiff_error;
+}
+
+namespace {
+
+enum : uint16_t { T_BYTE = 1, T_ASCII = 2, T_SHORT = 3, T_LONG = 4, T_DOUBLE = 12, T_LONG8 = 16 };
+
+struct Entry {
+    uint16_t tag, type;
+    uint64_t count;
+    std::vector<uint8_t> data;   // raw little-endian payload
+};
+
+template <typename T>
+void put(std::vector<uint8_t>& v, T x)
+{
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&x);
+    v.insert(v.end(), p, p + sizeof(T));
+}
+
+Entry shorts(uint16_t tag, const std::vector<uint16_t>& xs)
+{
+    Entry e{tag, T_SHORT, xs.size(), {}};
+    for (uint16_t x : xs) put(e.data, x);
+    return e;
+}
+Entry longs(uint16_t tag, const std::vector<uint32_t>& xs)
+{
+    Entry e{tag, T_LONG, xs.size(), {}};
+    for (uint32_t x : xs) put(e.data, x);
+    return e;
+}
+Entry doubles(uint16_t tag, const std::vector<double>& xs)
+{
+    Entry e{tag, T_DOUBLE, xs.size(), {}};
+    for (double x : xs) put(e.data, x);
+    return e;
+}
+Entry ascii(uint16_t tag, const std::string& s)
+{
+    Entry e{tag, T_ASCII, s.size() + 1, {}};
+    e.data.assign(s.begin(), s.end());
+    e.data.push_back(0);
+    return e;
+}
+Entry offsets(uint16_t tag, const std::vector<uint64_t>& xs, bool big)
+{
+    Entry e{tag, static_cast<uint16_t>(big ? T_LONG8 : T_LONG), xs.size(), {}};
+    for (uint64_t x : xs) { if (big) put(e.data, x); else put(e.data, static_cast<uint32_t>(x)); }
+    return e;
+}
+
+std::string xml_escape(const std::string& s)
+{
+    std::string o;
+    for (char c : s) {
+        if (c == '&') o += "&amp;"; else if (c == '<') o += "&lt;"; else if (c == '>') o += "&gt;";
+        else if (c == '"') o += "&quot;"; else o += c;
+    }
+    return o;
+}
+
+int fail(int code, const std::string& msg)
+{
+    pcrb::g_geotiff_error = msg;
+    return code;
+}
+
+}  // namespace
+
+extern "C" const char* pcr_geotiff_last_error(void) { return pcrb::g_geotiff_error.c_str(); }
+
+extern "C" int pcr_geotiff_write(const char* path, const float* const* bands, int32_t num_bands,
+                                 const pcr_grid_desc* grid, const char* const* band_names, int32_t epsg,
+                                 const char* compress, int32_t compress_level, int32_t tile_width,
+                                 int32_t tile_height, int32_t bigtiff)
+{
+    if (!path || !bands || !grid || num_bands <= 0)
+        return fail(PCR_INVALID_ARGUMENT, "write_geotiff: bad arguments");
+    const int W = grid->width, H = grid->height;
+    if (W <= 0 || H <= 0) return fail(PCR_INVALID_ARGUMENT, "grid dimensions mismatch config");
+    const std::string comp = compress ? compress : "NONE";
+    int compression = 1;
+    if (comp == "DEFLATE") compression = 8;
+    else if (!(comp == "NONE" || comp.empty()))
+        return fail(PCR_NOT_IMPLEMENTED, "write_geotiff: compression '" + comp + "' is not supported (NONE, DEFLATE)");
+    const int tw = tile_width > 0 ? (tile_width + 15) / 16 * 16 : 256;    // TIFF: tile dims multiple of 16
+    const int th = tile_height > 0 ? (tile_height + 15) / 16 * 16 : 256;
+    const int tiles_x = (W + tw - 1) / tw, tiles_y = (H + th - 1) / th;
+    const size_t per_band = static_cast<size_t>(tiles_x) * tiles_y;
+    const size_t raw_tile = static_cast<size_t>(tw) * th * sizeof(float);
+    const bool big = bigtiff != 0;
+    if (!big && static_cast<double>(per_band) * num_bands * raw_tile > 3.9e9)
+        return fail(PCR_INVALID_ARGUMENT, "write_geotiff: raster exceeds classic TIFF 4 GB limit; set bigtiff");
+
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(PCR_IO_ERROR, std::string("failed to create GeoTIFF: ") + path);
+
+    // header (IFD offset patched at the end: the IFD goes after the pixel data)
+    std::vector<uint8_t> hdr;
+    hdr.push_back('I'); hdr.push_back('I');
+    if (big) { put<uint16_t>(hdr, 43); put<uint16_t>(hdr, 8); put<uint16_t>(hdr, 0); put<uint64_t>(hdr, 0); }
+    else     { put<uint16_t>(hdr, 42); put<uint32_t>(hdr, 0); }
+    std::fwrite(hdr.data(), 1, hdr.size(), f);
+    uint64_t pos = hdr.size();
+
+    // tiles, band after band
+    std::vector<uint64_t> tile_off, tile_len;
+    std::vector<float> tile(static_cast<size_t>(tw) * th);
+    std::vector<uint8_t> zbuf(compression == 8 ? compressBound(raw_tile) : 0);
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    bool io_ok = true;
+    for (int b = 0; b < num_bands && io_ok; ++b) {
+        const float* src = bands[b];
+        for (int ty = 0; ty < tiles_y && io_ok; ++ty)
+            for (int tx = 0; tx < tiles_x && io_ok; ++tx) {
+                const int x0 = tx * tw, y0 = ty * th;
+                const int cw = std::min(tw, W - x0), chh = std::min(th, H - y0);
+                if (cw < tw || chh < th) std::fill(tile.begin(), tile.end(), nan);
+                for (int r = 0; r < chh; ++r)
+                    std::memcpy(&tile[static_cast<size_t>(r) * tw], src + static_cast<size_t>(y0 + r) * W + x0,
+                                static_cast<size_t>(cw) * sizeof(float));
+                const void* out = tile.data();
+                uint64_t len = raw_tile;
+                if (compression == 8) {
+                    uLongf zl = zbuf.size();
+                    if (compress2(zbuf.data(), &zl, reinterpret_cast<const Bytef*>(tile.data()), raw_tile,
+                                  std::max(1, std::min(9, compress_level))) != Z_OK) { io_ok = false; break; }
+                    out = zbuf.data(); len = zl;
+                }
+                tile_off.push_back(pos); tile_len.push_back(len);
+                io_ok = std::fwrite(out, 1, len, f) == len;
+                pos += len;
+                if (pos & 1) { std::fputc(0, f); ++pos; }          // word alignment
+            }
+    }
+    if (!io_ok) { std::fclose(f); return fail(PCR_IO_ERROR, "failed to write band data"); }
+
+    // tags
+    const uint16_t nb = static_cast<uint16_t>(num_bands);
+    std::vector<Entry> tags;
+    tags.push_back(longs(256, {static_cast<uint32_t>(W)}));
+    tags.push_back(longs(257, {static_cast<uint32_t>(H)}));
+    tags.push_back(shorts(258, std::vector<uint16_t>(nb, 32)));
+    tags.push_back(shorts(259, {static_cast<uint16_t>(compression)}));
+    tags.push_back(shorts(262, {1}));                                  // MinIsBlack
+    tags.push_back(shorts(277, {nb}));
+    tags.push_back(shorts(284, {static_cast<uint16_t>(nb > 1 ? 2 : 1)}));  // planar: separate planes
+    tags.push_back(longs(322, {static_cast<uint32_t>(tw)}));
+    tags.push_back(longs(323, {static_cast<uint32_t>(th)}));
+    tags.push_back(offsets(324, tile_off, big));
+    tags.push_back(offsets(325, tile_len, big));
+    if (nb > 1) tags.push_back(shorts(338, std::vector<uint16_t>(nb - 1, 0)));   // extra samples: unspecified
+    tags.push_back(shorts(339, std::vector<uint16_t>(nb, 3)));                   // IEEE float
+
+    // georeferencing: GridConfig::gdal_geotransform = [min_x, csx, 0, max_y, 0, csy]
+    const double ox = grid->min_x, oy = grid->max_y, sx = grid->cell_size_x, sy = grid->cell_size_y;
+    if (sx > 0 && sy < 0) {
+        tags.push_back(doubles(33550, {sx, -sy, 0.0}));
+        tags.push_back(doubles(33922, {0, 0, 0, ox, oy, 0}));
+    } else {
+        tags.push_back(doubles(34264, {sx, 0, 0, ox, 0, sy, 0, oy, 0, 0, 0, 0, 0, 0, 0, 1}));
+    }
+    std::vector<uint16_t> keys = {1, 1, 0, 0};
+    auto key = [&](uint16_t id, uint16_t value) { keys.insert(keys.end(), {id, 0, 1, value}); ++keys[3]; };
+    const bool geographic = epsg >= 4000 && epsg < 5000;
+    key(1024, epsg > 0 ? (geographic ? 2 : 1) : 32767);               // GTModelType
+    key(1025, 1);                                                      // RasterPixelIsArea
+    if (epsg > 0 && epsg < 65536) key(geographic ? 2048 : 3072, static_cast<uint16_t>(epsg));
+    tags.push_back(shorts(34735, keys));
+
+    std::string meta = "<GDALMetadata>\n";
+    for (int b = 0; b < num_bands; ++b)
+        if (band_names && band_names[b] && band_names[b][0])
+            meta += "  <Item name=\"DESCRIPTION\" sample=\"" + std::to_string(b) + "\" role=\"description\">" +
+                    xml_escape(band_names[b]) + "</Item>\n";
+    meta += "</GDALMetadata>\n";
+    tags.push_back(ascii(42112, meta));
+    tags.push_back(ascii(42113, "nan"));
+    std::sort(tags.begin(), tags.end(), [](const Entry& a, const Entry& b) { return a.tag < b.tag; });
+
+    // out-of-line payloads, then the IFD
+    const size_t inline_cap = big ? 8 : 4;
+    std::vector<uint64_t> where(tags.size(), 0);
+    for (size_t i = 0; i < tags.size(); ++i) {
+        if (tags[i].data.size() <= inline_cap) continue;
+        where[i] = pos;
+        std::fwrite(tags[i].data.data(), 1, tags[i].data.size(), f);
+        pos += tags[i].data.size();
+        if (pos & 1) { std::fputc(0, f); ++pos; }
+    }
+    if (!big && pos > 0xfffffff0ull) { std::fclose(f); return fail(PCR_INVALID_ARGUMENT, "classic TIFF overflow; set bigtiff"); }
+    const uint64_t ifd_pos = pos;
+    std::vector<uint8_t> ifd;
+    if (big) put<uint64_t>(ifd, tags.size()); else put<uint16_t>(ifd, static_cast<uint16_t>(tags.size()));
+    for (size_t i = 0; i < tags.size(); ++i) {
+        put<uint16_t>(ifd, tags[i].tag);
+        put<uint16_t>(ifd, tags[i].type);
+        if (big) put<uint64_t>(ifd, tags[i].count); else put<uint32_t>(ifd, static_cast<uint32_t>(tags[i].count));
+        std::vector<uint8_t> cell(inline_cap, 0);
+        if (tags[i].data.size() <= inline_cap) std::memcpy(cell.data(), tags[i].data.data(), tags[i].data.size());
+        else if (big) std::memcpy(cell.data(), &where[i], 8);
+        else { const uint32_t o = static_cast<uint32_t>(where[i]); std::memcpy(cell.data(), &o, 4); }
+        ifd.insert(ifd.end(), cell.begin(), cell.end());
+    }
+    if (big) put<uint64_t>(ifd, 0); else put<uint32_t>(ifd, 0);        // no next IFD
+    std::fwrite(ifd.data(), 1, ifd.size(), f);
+    std::fseek(f, big ? 8 : 4, SEEK_SET);
+    if (big) std::fwrite(&ifd_pos, 8, 1, f);
+    else { const uint32_t o = static_cast<uint32_t>(ifd_pos); std::fwrite(&o, 4, 1, f); }
+    if (std::fclose(f) != 0) return fail(PCR_IO_ERROR, "failed to close GeoTIFF");
+    return PCR_OK;
+}
+
+// Header reader: width, height, bands, EPSG and bounds of a (Big)TIFF written by
+// the function above or by GDAL with the same georeferencing tags.
+extern "C" int pcr_geotiff_read_info(const char* path, int32_t* width, int32_t* height, int32_t* num_bands,
+                                     int32_t* epsg, double bounds[4])
+{
+    if (!path || !width || !height || !num_bands || !epsg || !bounds)
+        return fail(PCR_INVALID_ARGUMENT, "read_geotiff_info: bad arguments");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(PCR_IO_ERROR, std::string("failed to open file: ") + path);
+    auto rd = [&](uint64_t off, void* dst, size_t n) {
+        return std::fseek(f, static_cast<long>(off), SEEK_SET) == 0 && std::fread(dst, 1, n, f) == n;
+    };
+    uint8_t h[16];
+    if (!rd(0, h, 8) || h[0] != 'I' || h[1] != 'I') { std::fclose(f); return fail(PCR_IO_ERROR, "not a little-endian TIFF"); }
+    uint16_t magic; std::memcpy(&magic, h + 2, 2);
+    const bool big = magic == 43;
+    if (!big && magic != 42) { std::fclose(f); return fail(PCR_IO_ERROR, "not a TIFF file"); }
+    uint64_t ifd = 0;
+    if (big) { if (!rd(8, &ifd, 8)) { std::fclose(f); return fail(PCR_IO_ERROR, "truncated TIFF"); } }
+    else { uint32_t o; std::memcpy(&o, h + 4, 4); ifd = o; }
+    uint64_t n = 0;
+    if (big) rd(ifd, &n, 8); else { uint16_t s = 0; rd(ifd, &s, 2); n = s; }
+    const size_t esz = big ? 20 : 12, inl = big ? 8 : 4;
+    *width = *height = 0; *num_bands = 1; *epsg = 0;
+    std::vector<double> scale, tie, xform;
+    std::vector<uint16_t> keys;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint8_t e[20];
+        if (!rd(ifd + (big ? 8 : 2) + i * esz, e, esz)) break;
+        uint16_t tag, type; std::memcpy(&tag, e, 2); std::memcpy(&type, e + 2, 2);
+        uint64_t count = 0;
+        if (big) std::memcpy(&count, e + 4, 8); else { uint32_t c; std::memcpy(&c, e + 4, 4); count = c; }
+        const size_t tsz = type == T_SHORT ? 2 : type == T_LONG ? 4 : (type == T_DOUBLE || type == T_LONG8) ? 8 : 1;
+        std::vector<uint8_t> payload(count * tsz);
+        const uint8_t* cell = e + (big ? 12 : 8);
+        if (payload.size() <= inl) std::memcpy(payload.data(), cell, payload.size());
+        else {
+            uint64_t off = 0;
+            if (big) std::memcpy(&off, cell, 8); else { uint32_t o; std::memcpy(&o, cell, 4); off = o; }
+            if (!rd(off, payload.data(), payload.size())) continue;
+        }
+        auto as_u = [&](size_t k) -> uint64_t {
+            if (type == T_SHORT) { uint16_t v; std::memcpy(&v, &payload[k * 2], 2); return v; }
+            if (type == T_LONG)  { uint32_t v; std::memcpy(&v, &payload[k * 4], 4); return v; }
+            if (type == T_LONG8) { uint64_t v; std::memcpy(&v, &payload[k * 8], 8); return v; }
+            return payload[k];
+        };
+        auto as_d = [&](std::vector<double>& out) {
+            out.resize(count);
+            if (type == T_DOUBLE) std::memcpy(out.data(), payload.data(), count * 8);
+        };
+        switch (tag) {
+        case 256: *width = static_cast<int32_t>(as_u(0)); break;
+        case 257: *height = static_cast<int32_t>(as_u(0)); break;
+        case 277: *num_bands = static_cast<int32_t>(as_u(0)); break;
+        case 33550: as_d(scale); break;
+        case 33922: as_d(tie); break;
+        case 34264: as_d(xform); break;
+        case 34735: keys.resize(count); for (size_t k = 0; k < count; ++k) keys[k] = static_cast<uint16_t>(as_u(k)); break;
+        default: break;
+        }
+    }
+    std::fclose(f);
+    for (size_t k = 4; k + 3 < keys.size(); k += 4)
+        if ((keys[k] == 3072 || keys[k] == 2048) && keys[k + 1] == 0) *epsg = keys[k + 3];
+    double gt[6] = {0, 1, 0, 0, 0, 1};
+    if (scale.size() >= 2 && tie.size() >= 6) {
+        gt[0] = tie[3] - tie[0] * scale[0]; gt[1] = scale[0]; gt[3] = tie[4] + tie[1] * scale[1]; gt[5] = -scale[1];
+    } else if (xform.size() >= 8) {
+        gt[0] = xform[3]; gt[1] = xform[0]; gt[3] = xform[7]; gt[5] = xform[5];
+    }
+    // same arithmetic as read_geotiff_info, src/io/grid_io.cpp:411-421
+    bounds[0] = gt[0];                       // min_x
+    bounds[3] = gt[3];                       // max_y
+    bounds[2] = gt[0] + gt[1] * *width;      // max_x
+    bounds[1] = gt[3] + gt[5] * *height;     // min_y
+    return PCR_OK;
+}

@@ -477,9 +477,11 @@ class PointCloud:
 
     # -- reference API ------------------------------------------------------
     @staticmethod
-    def create(capacity, loc=MemoryLocation.Host):
+    def create(capacity, loc=MemoryLocation.Host, device=0):
+        """`device` (new, default 0) selects the GPU for Device clouds; it must be the
+        pipeline's cuda_device_id."""
         try:
-            return PointCloud(capacity, loc)
+            return PointCloud(capacity, loc, device)
         except RuntimeError as e:
             print(f"PointCloud.create failed: {e}", file=sys.stderr)
             return None
@@ -563,15 +565,16 @@ class PointCloud:
             raise RuntimeError("Array size exceeds point count")
         self._store(c[1], np.float32, arr, name)
 
-    def _to(self, dst):
-        out = PointCloud(max(self._capacity, 1), dst, self._device)
+    def _to(self, dst, device=None):
+        dev = self._device if device is None else int(device)
+        out = PointCloud(max(self._capacity, 1), dst, dev)
         out._count = self._count
         out._crs = self._crs
         n = self._count
 
         def move(src, dst_storage, itemsize):
             check(lib.pcr_mem_copy(self._ptr(dst_storage), int(dst), self._ptr(src), int(self._loc),
-                                   n * itemsize, self._device))
+                                   n * itemsize, dev))
         move(self._x, out._x, 8)
         move(self._y, out._y, 8)
         for name, (desc, storage) in self._channels.items():
@@ -579,9 +582,9 @@ class PointCloud:
             move(storage, out._channels[name][1], np.dtype(_NP_DTYPE[desc.dtype]).itemsize)
         return out
 
-    def to_device(self):
+    def to_device(self, device=None):
         try:
-            return self._to(MemoryLocation.Device)
+            return self._to(MemoryLocation.Device, device)
         except RuntimeError as e:
             raise RuntimeError("Failed to transfer point cloud to Device memory. Possible causes: "
                                "CUDA out of memory, CUDA not initialized, or incompatible GPU "
@@ -923,6 +926,13 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
+def comm_slice_rows(height: int, world_size: int, rank: int):
+    """Rows [row0, row1) that `rank` merges and finalizes at an N-rank finalize."""
+    a, b = C.c_int32(0), C.c_int32(0)
+    check(lib.pcr_comm_slice_rows(int(height), int(world_size), int(rank), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 def device_count() -> int:
     return int(lib.pcr_device_count())
 
@@ -1023,5 +1033,5 @@ __all__ = [
     'gaussian_splat_spec', 'line_splat_spec', 'GeoTiffOptions', 'write_geotiff',
     'read_geotiff_info', 'PointCloudInfo', 'read_point_cloud', 'write_point_cloud',
     'read_point_cloud_info', 'PointCloudReader',
-    'comm_unique_id', 'device_count', 'device_name',
+    'comm_unique_id', 'comm_slice_rows', 'device_count', 'device_name',
 ]

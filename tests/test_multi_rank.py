@@ -1,0 +1,192 @@
+"""The N>1 path: points sharded by rank, partial grid states combined at finalize.
+
+CPU (gloo, world_size 2): the combine ALGORITHM — row-slice ownership from the product's own
+pcr_comm_slice_rows, all-to-all of partial record slices, Op::merge in rank order, touched-tile OR,
+all-gather of finalized slices — restated with the oracle's state arrays and torch.distributed, and
+checked against a single-rank run.  GPU (2+ devices): the real thing, NCCL + k_finalize, vs the oracle.
+"""
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import oracle as orc
+    import make_golden as mg
+    from pointcloud_raster_b200 import pcr
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    o = orc.Oracle()
+    w, h = 40, 37                                    # 37 rows over 2 ranks: uneven slices
+    gd = orc.GridDesc(0, 0, w, h, tile_width=16, tile_height=16)
+    rng = np.random.default_rng(123)
+    n = 20000
+    x, y = rng.uniform(-1, w + 1, n), rng.uniform(-1, h / 2, n)     # north tiles stay untouched
+    v = rng.normal(0, 5, n).astype(np.float32)
+    specs = [mg.Spec("v", t) for t in (orc.SUM, orc.MAX, orc.MIN, orc.AVERAGE, orc.COUNT)]
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    _, states, touched = o.run(gd, [(x[lo:hi], y[lo:hi], {"v": v[lo:hi]})], specs, return_state=True)
+
+    t_touched = torch.from_numpy(touched.astype(np.int32))
+    dist.all_reduce(t_touched, op=dist.ReduceOp.MAX)
+    touched_all = t_touched.numpy().astype(np.uint8)
+    cells = w * h
+    bands = []
+    for s, st in zip(specs, states):
+        k = o.lib.orc_state_floats(int(s.type))
+        st2 = st.reshape(k, cells)
+        r0, r1 = pcr.comm_slice_rows(h, world, rank)
+        # every rank sends slice j of its partial state to rank j
+        parts = [None] * world
+        for peer in range(world):
+            p0, p1 = pcr.comm_slice_rows(h, world, peer)
+            send = torch.from_numpy(np.ascontiguousarray(st2[:, p0 * w:p1 * w]))
+            recv = torch.empty(k, (r1 - r0) * w)
+            if peer == rank:
+                parts[rank] = send.numpy().copy()
+                continue
+            ops = [dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, recv, peer)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            parts[peer] = recv.numpy()
+        # owner merges the parts in RANK ORDER (Op::merge), then finalizes its slice
+        acc = np.ascontiguousarray(parts[0]).reshape(-1).copy()
+        sl_cells = (r1 - r0) * w
+        for peer in range(1, world):
+            src = np.ascontiguousarray(parts[peer]).reshape(-1)
+            o.lib.orc_state_merge(int(s.type), acc.ctypes.data, src.ctypes.data, sl_cells)
+        full_state = np.zeros(k * cells, np.float32).reshape(k, cells)
+        full_state[:, r0 * w:r1 * w] = acc.reshape(k, sl_cells)
+        out = np.empty((h, w), np.float32)
+        g = o.grid(gd)
+        o.lib.orc_finalize(C.byref(g), int(s.type), full_state.ctypes.data, touched_all.ctypes.data, out.ctypes.data)
+        mine = torch.from_numpy(out[r0:r1].copy())
+        gathered = [torch.empty((pcr.comm_slice_rows(h, world, p)[1] - pcr.comm_slice_rows(h, world, p)[0], w))
+                    for p in range(world)]
+        # all-gather with uneven slices: pad to the largest
+        m = max(g_.shape[0] for g_ in gathered)
+        padded = torch.zeros(m, w); padded[:mine.shape[0]] = mine
+        outl = [torch.zeros(m, w) for _ in range(world)]
+        dist.all_gather(outl, padded)
+        bands.append(np.concatenate([outl[p][:gathered[p].shape[0]].numpy() for p in range(world)], axis=0))
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "bands.npz"), *bands)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_combine_algorithm_gloo_world2(oracle):
+    import torch.multiprocessing as mp
+    import oracle as orc
+    import make_golden as mg
+    from util import compare_bands
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_gloo_worker, args=(world, _free_port(), d), nprocs=world, join=True)
+        z = np.load(os.path.join(d, "bands.npz"))
+        got = [z[f"arr_{i}"] for i in range(5)]
+    w, h = 40, 37
+    gd = orc.GridDesc(0, 0, w, h, tile_width=16, tile_height=16)
+    rng = np.random.default_rng(123)
+    n = 20000
+    x, y = rng.uniform(-1, w + 1, n), rng.uniform(-1, h / 2, n)
+    v = rng.normal(0, 5, n).astype(np.float32)
+    specs = [mg.Spec("v", t) for t in (orc.SUM, orc.MAX, orc.MIN, orc.AVERAGE, orc.COUNT)]
+    ref = oracle.run(gd, [(x, y, {"v": v})], specs)
+    compare_bands(oracle, gd, [(x, y, {"v": v})], specs, ref, got, "gloo world 2")
+    assert np.isnan(got[0][:16]).all()               # untouched north tiles: NaN on every rank's slice
+
+
+def test_slice_rows_cover_grid(pcr):
+    for h in (1, 2, 7, 37, 1000, 20000):
+        for world in (1, 2, 3, 4, 8):
+            edges = [pcr.comm_slice_rows(h, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == h
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            assert all(0 <= a <= b <= h for a, b in edges)
+
+
+# ---- the real N>1 path on GPUs ------------------------------------------------------------------
+def _gpu_worker(rank, world, id_path, out_dir, deterministic):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import time
+    from pointcloud_raster_b200 import pcr
+    from util import make_grid, spec, cloud as mk
+    if rank == 0:
+        open(id_path + ".tmp", "wb").write(pcr.comm_unique_id())
+        os.rename(id_path + ".tmp", id_path)
+    while not os.path.exists(id_path):
+        time.sleep(0.01)
+    uid = open(id_path, "rb").read()
+    gc = make_grid(pcr, 300, 211, tile=64)
+    rng = np.random.default_rng(77)
+    n = 400_000
+    x, y = rng.uniform(-2, 302, n), rng.uniform(-2, 120, n)
+    ch = {"value": rng.normal(0, 3, n).astype(np.float32), "hl": rng.uniform(0, 8, n).astype(np.float32)}
+    R = pcr.ReductionType
+    specs = [spec(pcr, "value", t) for t in (R.Sum, R.Max, R.Min, R.Average, R.Count)]
+    if not deterministic:
+        specs.append(pcr.line_splat_spec("value", default_direction=0.3, half_length_channel="hl", max_radius_cells=9.0))
+        specs.append(pcr.gaussian_splat_spec("value", default_sigma=1.5, max_radius_cells=5.0))
+    cfg = pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = specs; cfg.exec_mode = pcr.ExecutionMode.GPU
+    cfg.cuda_device_id = rank; cfg.deterministic = deterministic
+    p = pcr.Pipeline.create(cfg)
+    assert p is not None
+    p.comm_init(uid, rank, world)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    p.ingest(mk(pcr, x[lo:hi], y[lo:hi], {k: v[lo:hi] for k, v in ch.items()}))
+    p.finalize()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), *[np.array(p.result().band_array(i)) for i in range(len(specs))])
+    p.comm_barrier()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic):
+    if gpu_pcr.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import multiprocessing as mp
+    import oracle as orc
+    from util import make_grid, spec, compare_bands, grid_desc
+    world = min(gpu_pcr.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as d:
+        procs = [ctx.Process(target=_gpu_worker, args=(r, world, os.path.join(d, "id"), d, deterministic))
+                 for r in range(world)]
+        for pr in procs: pr.start()
+        for pr in procs: pr.join(300)
+        assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+        per_rank = []
+        for r in range(world):
+            z = np.load(os.path.join(d, f"rank{r}.npz"))
+            per_rank.append([z[k] for k in sorted(z.files, key=lambda s: int(s.split("_")[1]))])
+    for r in range(1, world):                          # every rank ends with the same complete bands
+        for a, b in zip(per_rank[0], per_rank[r]):
+            assert np.array_equal(a, b, equal_nan=True)
+    pcr = gpu_pcr
+    gc = make_grid(pcr, 300, 211, tile=64)
+    rng = np.random.default_rng(77)
+    n = 400_000
+    x, y = rng.uniform(-2, 302, n), rng.uniform(-2, 120, n)
+    ch = {"value": rng.normal(0, 3, n).astype(np.float32), "hl": rng.uniform(0, 8, n).astype(np.float32)}
+    R = pcr.ReductionType
+    specs = [spec(pcr, "value", t) for t in (R.Sum, R.Max, R.Min, R.Average, R.Count)]
+    if not deterministic:
+        specs.append(pcr.line_splat_spec("value", default_direction=0.3, half_length_channel="hl", max_radius_cells=9.0))
+        specs.append(pcr.gaussian_splat_spec("value", default_sigma=1.5, max_radius_cells=5.0))
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, [(x, y, ch)], specs)
+    compare_bands(oracle, gd, [(x, y, ch)], specs, ref, per_rank[0], f"{world} GPUs", device_weights=True)
