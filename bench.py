@@ -136,6 +136,8 @@ def build_pipeline(pcr, device, async_ingest, rank=0, world=1, unique_id=None):
     cfg.async_ingest = async_ingest
     cfg.point_kernel = int(os.environ.get("PCR_POINT_KERNEL", "0"))
     cfg.warp_aggregate = int(os.environ.get("PCR_WARP_AGG", "0"))
+    cfg.comm_mode = int(os.environ.get("PCR_COMM_MODE", "0"))
+    cfg.comm_root_only = bool(int(os.environ.get("PCR_COMM_ROOT_ONLY", "0")))
     p = pcr.Pipeline.create(cfg)
     if p is None:
         raise RuntimeError("Pipeline.create failed (no CPU fallback exists)")

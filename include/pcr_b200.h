@@ -99,6 +99,12 @@ typedef struct pcr_pipeline_desc {
     int32_t                   staging_threads;      /* host copy threads, 0 = default */
     int32_t                   point_kernel;         /* 0 = auto, 1 = direct LDG, 2 = TMA-staged persistent */
     int32_t                   warp_aggregate;       /* 0 = auto (adaptive run aggregation), 2 = off */
+    int32_t                   gaussian_kernel;      /* 0 = auto, 1 = scatter (warp per point, REDs),
+                                                       2 = gather (tile-binned, atomic-free, deterministic) */
+    int32_t                   comm_mode;            /* N>1 combine: 0 = auto (peer memory over NVLink when every
+                                                       GPU pair has P2P access, else NCCL), 1 = NCCL, 2 = peer */
+    int32_t                   comm_root_only;       /* 1 = only rank 0 ends with complete bands (other ranks
+                                                       keep their own row slice) */
     int32_t                   async_ingest;         /* 1 = device-resident ingests return without a
                                                        stream sync; buffers must stay valid until the
                                                        next finalize / synchronize */

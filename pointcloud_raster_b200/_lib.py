@@ -47,6 +47,7 @@ class PipelineDesc(C.Structure):
                 ("deterministic", C.c_int32), ("ring_depth", C.c_int32),
                 ("ring_slot_points", C.c_uint64), ("staging_threads", C.c_int32),
                 ("point_kernel", C.c_int32), ("warp_aggregate", C.c_int32),
+                ("gaussian_kernel", C.c_int32), ("comm_mode", C.c_int32), ("comm_root_only", C.c_int32),
                 ("async_ingest", C.c_int32)]
 
 

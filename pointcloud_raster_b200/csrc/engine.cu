@@ -262,6 +262,9 @@ Status Engine::init(const pcr_pipeline_desc& d)
     async_device_ingest_ = d.async_ingest != 0;
     point_variant_ = d.point_kernel == 2 ? POINT_TMA : d.point_kernel == 1 ? POINT_DIRECT : POINT_DIRECT;
     warp_aggregate_ = d.warp_aggregate != 2;
+    gaussian_variant_ = d.gaussian_kernel;
+    comm_mode_ = d.comm_mode;
+    gather_root_only_ = d.comm_root_only != 0;
     slot_points_ = d.ring_slot_points ? static_cast<size_t>(d.ring_slot_points) : (size_t(1) << 20);
     slot_points_ = align_up(slot_points_, 1024);
     const int depth = d.ring_depth > 0 ? d.ring_depth : 3;
@@ -347,9 +350,10 @@ Status Engine::init(const pcr_pipeline_desc& d)
     ST_TRY(plan());
     if (deterministic_)
         for (const Pass& p : passes_)
-            if (p.glyph.type != PCR_GLYPH_POINT)
+            if (p.glyph.type == PCR_GLYPH_LINE || (p.glyph.type == PCR_GLYPH_GAUSSIAN && !use_gather(p)))
                 return Status::error(PCR_NOT_IMPLEMENTED,
-                                     "pipeline: deterministic mode covers the Point glyph only");
+                                     "pipeline: deterministic mode covers the Point glyph and the Gaussian "
+                                     "gather kernel, not the Line glyph / Gaussian scatter kernel");
     ST_TRY(alloc_state());
     ST_TRY(init_state());
     CU_TRY(cudaStreamSynchronize(compute_));
@@ -401,10 +405,13 @@ Engine::~Engine()
         if (copy_) cudaStreamSynchronize(copy_);
         if (compute_) cudaStreamSynchronize(compute_);
     }
+    peer_unmap();
     if (comm_) engine_comm_destroy(nccl_, comm_);
     for (Pass& p : passes_) { cudaFree(p.d_state); cudaFree(p.d_combined); }
     cudaFree(d_touched_);
     cudaFree(d_touched_all_);
+    cudaFree(d_flags_);
+    cudaFree(d_touched_stage_);
     cudaFree(d_out_);
     if (h_out_) cudaFreeHost(h_out_);
     for (Slot& s : ring_) {
@@ -413,6 +420,8 @@ Engine::~Engine()
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.kernel_done) cudaEventDestroy(s.kernel_done);
     }
+    cudaFree(gs_.keys); cudaFree(gs_.keys_alt); cudaFree(gs_.idx); cudaFree(gs_.idx_alt);
+    cudaFree(gs_.sort_tmp); cudaFree(gs_.records); cudaFree(gs_.aux);
     cudaFree(d_sort_tmp_); cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_idx_); cudaFree(d_idx_alt_);
     for (auto& sp : prof_open_) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& ev : prof_free_) cudaEventDestroy(ev);
@@ -597,13 +606,46 @@ Status Engine::ingest(const double* x, const double* y, size_t n, const pcr_chan
     return Status::success();
 }
 
+bool Engine::use_gather(const Pass& p) const
+{
+    if (p.glyph.type != PCR_GLYPH_GAUSSIAN || !gauss_gather_supported(p.layout)) return false;
+    if (gaussian_variant_ == 1) return false;
+    if (gaussian_variant_ == 2) return true;
+    // auto: the scatter kernel unless bit-reproducibility was asked for (measured on B200, 5M points,
+    // 1000x1000: sigma=16 gather 59 ms vs scatter 61 ms, sigma=4 gather 18.7 ms vs scatter 12.5 ms)
+    return deterministic_;
+}
+
+Status Engine::ensure_gauss_scratch(size_t n, size_t record_bytes)
+{
+    if (n <= gs_.capacity && record_bytes <= gs_.record_bytes) return Status::success();
+    CU_TRY(cudaStreamSynchronize(compute_));
+    cudaFree(gs_.keys); cudaFree(gs_.keys_alt); cudaFree(gs_.idx); cudaFree(gs_.idx_alt);
+    cudaFree(gs_.sort_tmp); cudaFree(gs_.records); cudaFree(gs_.aux);
+    gs_ = GaussScratch{};
+    const size_t cap = std::max(n, std::min(slot_points_, size_t(1) << 22));
+    const size_t rb = std::max<size_t>(record_bytes, 64);
+    gs_.sort_tmp_bytes = gauss_sort_temp_bytes(cap, gp_);
+    CU_TRY(cudaMalloc(&gs_.sort_tmp, std::max<size_t>(gs_.sort_tmp_bytes, 16)));
+    CU_TRY(cudaMalloc(&gs_.keys, cap * 4));
+    CU_TRY(cudaMalloc(&gs_.keys_alt, cap * 4));
+    CU_TRY(cudaMalloc(&gs_.idx, cap * 4));
+    CU_TRY(cudaMalloc(&gs_.idx_alt, cap * 4));
+    CU_TRY(cudaMalloc(&gs_.records, cap * rb));
+    CU_TRY(cudaMalloc(&gs_.aux, 2 * sizeof(int)));
+    gs_.capacity = cap;
+    gs_.record_bytes = rb;
+    return Status::success();
+}
+
 // Launches every pass over one device-resident chunk on the compute stream.
 Status Engine::run_passes(const double* dx, const double* dy, size_t n,
                           const std::vector<const float*>& cp)
 {
-    if (deterministic_) return run_passes_deterministic(dx, dy, n, cp);
+    if (deterministic_) ST_TRY(run_passes_deterministic(dx, dy, n, cp));
     prof_begin(PROF_ACC, compute_);
     for (Pass& p : passes_) {
+        if (deterministic_ && p.glyph.type == PCR_GLYPH_POINT) continue;   // folded by the sort path above
         ChannelPtrs ch{};
         for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])];
         if (p.glyph.type == PCR_GLYPH_POINT) {
@@ -624,7 +666,23 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
             g.max_radius_cells = p.glyph.max_radius_cells;
             if (p.glyph.type == PCR_GLYPH_LINE)
                 CU_TRY(launch_line_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
-            else
+            else if (use_gather(p)) {
+                // bounded sub-chunks keep the sort / record scratch small
+                const size_t kSub = size_t(1) << 22;
+                for (size_t q0 = 0; q0 < n; q0 += kSub) {
+                    const size_t cnt = std::min(kSub, n - q0);
+                    ST_TRY(ensure_gauss_scratch(cnt, gauss_record_bytes(p.layout)));
+                    ChannelPtrs c2 = ch;
+                    for (size_t c = 0; c < p.channels.size(); ++c) c2.p[c] = ch.p[c] + q0;
+                    GlyphParams g2 = g;
+                    if (g2.sigma_x) g2.sigma_x += q0;
+                    if (g2.sigma_y) g2.sigma_y += q0;
+                    if (g2.rotation) g2.rotation += q0;
+                    CU_TRY(launch_gaussian_gather(compute_, dx + q0, dy + q0, c2, g2, cnt, p.d_state, gp_, p.layout,
+                                                  d_touched_, gs_, sm_count_));
+                    launches_ += 4;   // keys, sort, records, gather
+                }
+            } else
                 CU_TRY(launch_gaussian_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
             ++launches_;
         }
@@ -752,7 +810,10 @@ Status Engine::finalize_single()
         StateParts parts{};
         parts.part[0] = p.d_state;
         parts.n = 1;
-        CU_TRY(launch_finalize(compute_, parts, 0, 0, cells_, d_out_, cells_, gp_, p.layout, p.fin, d_touched_));
+        OutTargets outs{};
+        outs.out[0] = d_out_;
+        outs.n = 1;
+        CU_TRY(launch_finalize(compute_, parts, 0, 0, cells_, outs, cells_, gp_, p.layout, p.fin, d_touched_));
         ++launches_;
     }
     prof_end(compute_);

@@ -79,7 +79,23 @@ private:
     bool stop_ = false;
 };
 
-struct NcclApi;   // dlopen'ed subset of NCCL (engine_comm.cu)
+struct NcclApi;   // dlopen'ed subset of NCCL (engine_ext.cu)
+
+// device scratch of the Gaussian gather path (gauss_gather.cu)
+struct GaussScratch {
+    uint32_t *keys = nullptr, *keys_alt = nullptr, *idx = nullptr, *idx_alt = nullptr;
+    void* sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    uint32_t* records = nullptr;
+    int* aux = nullptr;              // {max footprint radius, tile counter}
+    size_t capacity = 0, record_bytes = 0;
+};
+bool gauss_gather_supported(const PassLayout& L);
+size_t gauss_record_bytes(const PassLayout& L);
+size_t gauss_sort_temp_bytes(size_t n, const GridParams& g);
+cudaError_t launch_gaussian_gather(cudaStream_t s, const double* x, const double* y, const ChannelPtrs& ch,
+                                   const GlyphParams& gp, size_t n, uint32_t* state, const GridParams& g,
+                                   const PassLayout& L, uint32_t* touched, GaussScratch& sc, int sm_count);
 
 class Engine {
 public:
@@ -122,6 +138,10 @@ private:
                        const std::vector<const float*>& chan_ptrs, bool pinned);
     Status finalize_single();
     Status finalize_multi();
+    Status finalize_multi_nccl();
+    Status finalize_multi_peer();
+    Status peer_map();               // exchange CUDA IPC handles, map every rank's buffers
+    void peer_unmap();
     int channel_slot(const std::string& name);
 
     // profiling helpers
@@ -173,6 +193,10 @@ private:
     uint32_t *d_keys_ = nullptr, *d_keys_alt_ = nullptr, *d_idx_ = nullptr, *d_idx_alt_ = nullptr;
     size_t sort_capacity_ = 0;
     Status ensure_sort_scratch(size_t n);
+    GaussScratch gs_;
+    int gaussian_variant_ = 0;       // 0 auto, 1 scatter (warp per point), 2 gather
+    Status ensure_gauss_scratch(size_t n, size_t record_bytes);
+    bool use_gather(const Pass& p) const;
 
     // ---- stats / progress ----
     uint64_t collections_ = 0, points_ = 0;
@@ -195,6 +219,20 @@ private:
     NcclApi* nccl_ = nullptr;
     void* comm_ = nullptr;
     int rank_ = 0, world_ = 1;
+    // peer-memory path: every rank's state / touched / bands / flags mapped into this process
+    bool peer_ok_ = false;
+    int comm_mode_ = 0;               // 0 auto (peer memory when every pair has P2P), 1 NCCL, 2 peer
+    bool gather_root_only_ = false;
+    struct PeerBuffers {
+        std::vector<uint32_t*> combined;   // one per pass: kMaxParts slots of max_slice cells
+        uint32_t* touched_stage = nullptr; // [world][n_tiles]
+        float* out = nullptr;
+        uint32_t* flags = nullptr;
+    };
+    uint32_t* d_touched_stage_ = nullptr;
+    PeerBuffers peer_[kMaxParts];
+    uint32_t* d_flags_ = nullptr;     // [2 phases][kMaxParts]
+    uint32_t epoch_ = 0;
 };
 
 // deterministic path (det_kernels.cu)

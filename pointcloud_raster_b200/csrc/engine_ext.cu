@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace pcrb {
@@ -65,6 +66,7 @@ Status Engine::run_passes_deterministic(const double* dx, const double* dy, size
         launches_ += 2;   // key build + radix sort (CUB launches several kernels; counted as one)
         prof_begin(PROF_ACC, compute_);
         for (Pass& p : passes_) {
+            if (p.glyph.type != PCR_GLYPH_POINT) continue;      // glyph passes run in run_passes
             ChannelPtrs ch{};
             for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])] + p0;
             CU_TRY(det_point_reduce(compute_, d_keys_, d_idx_, cnt, ch, p.d_state, p.layout,
@@ -91,6 +93,7 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int dtype, int peer, void* comm, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int dtype, int peer, void* comm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int dtype, int op, void* comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int dtype, void* comm, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     // ncclDataType_t / ncclRedOp_t values (nccl.h)
     static constexpr int kUint32 = 3, kFloat32 = 7, kUint8 = 1;
@@ -118,9 +121,10 @@ static NcclApi* nccl_load(std::string& err)
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.GroupStart || !api.GroupEnd ||
-        !api.Send || !api.Recv || !api.AllReduce || !api.GetErrorString) {
+        !api.Send || !api.Recv || !api.AllReduce || !api.AllGather || !api.GetErrorString) {
         err = "libnccl.so.2 lacks a required symbol";
         api.handle = nullptr;
         return nullptr;
@@ -168,7 +172,193 @@ Status Engine::comm_init(const void* id128, int rank, int world)
     rank_ = rank;
     world_ = world;
     CU_TRY(cudaMalloc(&d_touched_all_, std::max(1, n_tiles_) * sizeof(uint32_t)));
+    if (comm_mode_ != 1) {
+        Status s = peer_map();
+        if (!s.ok() && comm_mode_ == 2) return s;     // peer memory was demanded
+    }
     return Status::success();
+}
+
+// ---------------------------------------------------------------------------
+// Peer-memory path: map every rank's state / touched / band / flag buffers with CUDA IPC so
+// that the merge+finalize kernel reads the peers' partial records straight over NVLink and
+// stores the finalized slice straight into the peers' band arrays — no staging buffer, no
+// separate collective.  NCCL is used once, to all-gather the 64-byte IPC handles.
+// ---------------------------------------------------------------------------
+Status Engine::peer_map()
+{
+    peer_ok_ = false;
+    // all ranks must agree: 1 iff this rank can reach every other device
+    int can_all = 1;
+    std::vector<int> devs(world_, 0);
+    {
+        int* d_dev = nullptr;
+        CU_TRY(cudaMalloc(&d_dev, sizeof(int) * world_));
+        CU_TRY(cudaMemcpyAsync(d_dev + rank_, &device_, sizeof(int), cudaMemcpyHostToDevice, compute_));
+        NC_TRY(nccl_->AllGather(d_dev + rank_, d_dev, sizeof(int), NcclApi::kUint8, comm_, compute_));
+        CU_TRY(cudaMemcpyAsync(devs.data(), d_dev, sizeof(int) * world_, cudaMemcpyDeviceToHost, compute_));
+        CU_TRY(cudaStreamSynchronize(compute_));
+        for (int k = 0; k < world_; ++k) {
+            if (k == rank_) continue;
+            int ok = 0;
+            if (devs[k] == device_ || cudaDeviceCanAccessPeer(&ok, device_, devs[k]) != cudaSuccess || !ok) can_all = 0;
+        }
+        CU_TRY(cudaMemcpyAsync(d_dev, &can_all, sizeof(int), cudaMemcpyHostToDevice, compute_));
+        NC_TRY(nccl_->AllReduce(d_dev, d_dev, 1, NcclApi::kUint32, /*ncclMin*/ 3, comm_, compute_));
+        CU_TRY(cudaMemcpyAsync(&can_all, d_dev, sizeof(int), cudaMemcpyDeviceToHost, compute_));
+        CU_TRY(cudaStreamSynchronize(compute_));
+        cudaFree(d_dev);
+    }
+    if (!can_all)
+        return Status::error(PCR_CUDA_ERROR, "pipeline: peer-memory combine needs P2P access between all ranks' GPUs");
+
+    if (!d_flags_) {
+        CU_TRY(cudaMalloc(&d_flags_, (2 * kMaxParts + 4) * sizeof(uint32_t)));   // + the done counter
+        CU_TRY(cudaMemsetAsync(d_flags_, 0, (2 * kMaxParts + 4) * sizeof(uint32_t), compute_));
+    }
+    // combine buffers (the push targets) and touched staging, one slot per rank
+    const size_t rows_per = (static_cast<size_t>(grid_.height) + world_ - 1) / world_;
+    const size_t max_slice = rows_per * static_cast<size_t>(grid_.width);
+    for (Pass& p : passes_)
+        if (!p.d_combined)
+            CU_TRY(cudaMalloc(&p.d_combined, static_cast<size_t>(world_) * max_slice * p.layout.width * 4));
+    if (!d_touched_stage_) {
+        CU_TRY(cudaMalloc(&d_touched_stage_, static_cast<size_t>(world_) * std::max(1, n_tiles_) * 4));
+        CU_TRY(cudaMemsetAsync(d_touched_stage_, 0, static_cast<size_t>(world_) * std::max(1, n_tiles_) * 4, compute_));
+    }
+    // handles: [pass combine buffers..., touched staging, out, flags]
+    const size_t n_buf = passes_.size() + 3;
+    std::vector<cudaIpcMemHandle_t> mine(n_buf);
+    for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(cudaIpcGetMemHandle(&mine[i], passes_[i].d_combined));
+    CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size()], d_touched_stage_));
+    CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 1], d_out_));
+    CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 2], d_flags_));
+    const size_t bytes = n_buf * sizeof(cudaIpcMemHandle_t);
+    std::vector<cudaIpcMemHandle_t> all(n_buf * world_);
+    unsigned char* d_h = nullptr;
+    CU_TRY(cudaMalloc(&d_h, bytes * world_));
+    CU_TRY(cudaMemcpyAsync(d_h + bytes * rank_, mine.data(), bytes, cudaMemcpyHostToDevice, compute_));
+    NC_TRY(nccl_->AllGather(d_h + bytes * rank_, d_h, bytes, NcclApi::kUint8, comm_, compute_));
+    CU_TRY(cudaMemcpyAsync(all.data(), d_h, bytes * world_, cudaMemcpyDeviceToHost, compute_));
+    CU_TRY(cudaStreamSynchronize(compute_));
+    cudaFree(d_h);
+
+    for (int k = 0; k < world_; ++k) {
+        PeerBuffers& pb = peer_[k];
+        pb.combined.assign(passes_.size(), nullptr);
+        if (k == rank_) {
+            for (size_t i = 0; i < passes_.size(); ++i) pb.combined[i] = passes_[i].d_combined;
+            pb.touched_stage = d_touched_stage_; pb.out = d_out_; pb.flags = d_flags_;
+            continue;
+        }
+        const cudaIpcMemHandle_t* h = &all[n_buf * k];
+        auto open = [&](const cudaIpcMemHandle_t& hh, void** out) {
+            return cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess);
+        };
+        for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(open(h[i], reinterpret_cast<void**>(&pb.combined[i])));
+        CU_TRY(open(h[passes_.size()], reinterpret_cast<void**>(&pb.touched_stage)));
+        CU_TRY(open(h[passes_.size() + 1], reinterpret_cast<void**>(&pb.out)));
+        CU_TRY(open(h[passes_.size() + 2], reinterpret_cast<void**>(&pb.flags)));
+    }
+    // nobody may signal into a flag array that is not zeroed yet / unmap-safe start
+    NC_TRY(nccl_->AllReduce(d_touched_all_, d_touched_all_, 1, NcclApi::kUint32, NcclApi::kMax, comm_, compute_));
+    CU_TRY(cudaStreamSynchronize(compute_));
+    peer_ok_ = true;
+    return Status::success();
+}
+
+void Engine::peer_unmap()
+{
+    if (!peer_ok_) return;
+    cudaSetDevice(device_);
+    if (comm_ && nccl_) {   // every rank must be done with everyone's memory before it is unmapped/freed
+        nccl_->AllReduce(d_touched_all_, d_touched_all_, 1, NcclApi::kUint32, NcclApi::kMax, comm_, compute_);
+        cudaStreamSynchronize(compute_);
+    }
+    for (int k = 0; k < world_; ++k) {
+        if (k == rank_) continue;
+        for (uint32_t* p : peer_[k].combined) if (p) cudaIpcCloseMemHandle(p);
+        if (peer_[k].touched_stage) cudaIpcCloseMemHandle(peer_[k].touched_stage);
+        if (peer_[k].out) cudaIpcCloseMemHandle(peer_[k].out);
+        if (peer_[k].flags) cudaIpcCloseMemHandle(peer_[k].flags);
+    }
+    if (comm_ && nccl_) {   // ... and every mapping must be closed before the owners free the memory
+        nccl_->AllReduce(d_touched_all_, d_touched_all_, 1, NcclApi::kUint32, NcclApi::kMax, comm_, compute_);
+        cudaStreamSynchronize(compute_);
+    }
+    peer_ok_ = false;
+}
+
+// N>1 finalize over peer memory.  Per call, all on the compute stream, no host sync:
+//   k_push_slices   every record I hold for a row slice owned by rank j is stored straight into
+//                   rank j's combine buffer (posted NVLink writes), my touched-tile flags into
+//                   everyone's staging; the last CTA releases phase 0 on every rank
+//   k_finalize_peer waits until all ranks' pushes have landed here, merges the `world` parts of
+//                   my slice in rank order (Op::merge), finalizes, stores the bands into my array
+//                   and the peers' arrays; the last CTA releases phase 1
+//   k_peer_wait     phase 1 from everyone: my combine buffer, my state and my bands are mine
+//                   again, the next ingest may run.
+Status Engine::finalize_multi_peer()
+{
+    ++epoch_;
+    PeerSync ps{};
+    ps.pf.n = world_; ps.pf.rank = rank_;
+    ps.pt.n = world_;
+    ps.epoch = epoch_;
+    ps.done_counter = reinterpret_cast<unsigned int*>(d_flags_ + 2 * kMaxParts);
+    for (int k = 0; k < world_; ++k) {
+        ps.pf.flags[k] = peer_[k].flags;
+        ps.pt.touched[k] = d_touched_stage_ + static_cast<size_t>(k) * n_tiles_;   // local staging
+    }
+    const size_t rows_per = (static_cast<size_t>(grid_.height) + world_ - 1) / world_;
+    const size_t max_slice = rows_per * static_cast<size_t>(grid_.width);
+    int r0, r1;
+    slice_rows(grid_.height, world_, rank_, r0, r1);
+    const size_t my0 = static_cast<size_t>(r0) * grid_.width, my_cells = static_cast<size_t>(r1 - r0) * grid_.width;
+
+    prof_begin(PROF_FIN, compute_);
+    if (passes_.empty()) CU_TRY(launch_peer_signal(compute_, ps.pf, 0, epoch_));
+    for (size_t i = 0; i < passes_.size(); ++i) {
+        PushTargets pt{};
+        for (int k = 0; k < world_; ++k) { pt.combined[k] = peer_[k].combined[i]; pt.touched_stage[k] = peer_[k].touched_stage; }
+        pt.rows_per = static_cast<int>(rows_per);
+        pt.max_slice_cells = max_slice;
+        CU_TRY(launch_push_slices(compute_, passes_[i].d_state, d_touched_, n_tiles_, gp_, passes_[i].layout, pt, ps,
+                                  i == 0, i + 1 == passes_.size()));
+        ++launches_;
+    }
+    for (size_t i = 0; i < reductions_.size(); ++i)
+        if (reductions_[i].rejected)
+            CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), compute_));
+    OutTargets outs{};
+    outs.out[outs.n++] = d_out_;
+    for (int k = 0; k < world_; ++k) {
+        if (k == rank_) continue;
+        if (gather_root_only_ && k != 0) continue;
+        outs.out[outs.n++] = peer_[k].out;
+    }
+    if (passes_.empty()) CU_TRY(launch_peer_signal(compute_, ps.pf, 1, epoch_));
+    for (size_t i = 0; i < passes_.size(); ++i) {
+        Pass& p = passes_[i];
+        const size_t W = p.layout.width;
+        StateParts parts{};
+        parts.n = world_;
+        for (int k = 0; k < world_; ++k)
+            parts.part[k] = (k == rank_) ? p.d_state + my0 * W : p.d_combined + static_cast<size_t>(k) * max_slice * W;
+        ps.signal_begin = 0;
+        ps.signal_end = i + 1 == passes_.size();
+        CU_TRY(launch_finalize_peer(compute_, parts, my0, my0, my_cells, outs, cells_, gp_, p.layout, p.fin, ps));
+        ++launches_;
+    }
+    prof_end(compute_);
+    CU_TRY(launch_peer_wait(compute_, ps.pf, 1, epoch_));
+    ++launches_;
+    return Status::success();
+}
+
+Status Engine::finalize_multi()
+{
+    return peer_ok_ ? finalize_multi_peer() : finalize_multi_nccl();
 }
 
 Status Engine::comm_barrier()
@@ -188,7 +378,7 @@ Status Engine::comm_barrier()
 // (Op::merge, builtin_ops.h:15,28,41,54,67,95-97 — fixed order, so the float sums
 // do not depend on arrival order); the finalized slices are then exchanged so
 // every rank ends with complete bands.
-Status Engine::finalize_multi()
+Status Engine::finalize_multi_nccl()
 {
     const size_t rows_per = (static_cast<size_t>(grid_.height) + world_ - 1) / world_;
     auto row0 = [&](int k) -> size_t { int a, b; slice_rows(grid_.height, world_, std::min(k, world_ - 1), a, b);
@@ -222,7 +412,10 @@ Status Engine::finalize_multi()
         for (int k = 0; k < world_; ++k)
             parts.part[k] = (k == rank_) ? p.d_state + my0 * W : p.d_combined + static_cast<size_t>(k) * max_slice * W;
         prof_begin(PROF_FIN, compute_);
-        CU_TRY(launch_finalize(compute_, parts, my0, my0, my_cells, d_out_, cells_, gp_, p.layout, p.fin, d_touched_all_));
+        OutTargets outs{};
+        outs.out[0] = d_out_;
+        outs.n = 1;
+        CU_TRY(launch_finalize(compute_, parts, my0, my0, my_cells, outs, cells_, gp_, p.layout, p.fin, d_touched_all_));
         ++launches_;
         prof_end(compute_);
     }

@@ -25,6 +25,13 @@ struct StateParts {
     int n;
 };
 
+// Where a finalized slice is stored: the rank's own band array, plus (peer-memory path)
+// the band arrays of other ranks mapped over NVLink.
+struct OutTargets {
+    float* out[kMaxParts];
+    int n;
+};
+
 enum PointKernelVariant { POINT_DIRECT = 1, POINT_TMA = 2 };
 
 // state identity fill (init_state_kernel<Op>, src/engine/grid_merge.cu:16-23)
@@ -53,8 +60,55 @@ cudaError_t launch_gaussian_accumulate(cudaStream_t s, const double* x, const do
 // merge (Op::merge over parts) + finalize (Op::finalize) + touched-tile NaN rule,
 // for cells [cell0, cell0+count); writes out[band*band_stride + cell].
 cudaError_t launch_finalize(cudaStream_t s, const StateParts& parts, size_t part_cell0,
-                            size_t cell0, size_t count, float* out, size_t band_stride,
+                            size_t cell0, size_t count, const OutTargets& out, size_t band_stride,
                             const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
                             const uint32_t* touched);
+
+// ---- peer-memory combine (one process per GPU, buffers mapped with CUDA IPC) ----
+// flags layout on every rank: flags[phase * kMaxParts + writer_rank], written by the peers.
+struct PeerFlags {
+    uint32_t* flags[kMaxParts];      // every rank's flag array (own one included)
+    int n, rank;
+};
+struct PeerTouched {
+    const uint32_t* touched[kMaxParts];
+    int n;
+};
+// Peer handshake fused into the finalize kernel (N>1, peer-memory path).
+struct PeerSync {
+    PeerFlags pf;
+    PeerTouched pt;
+    uint32_t epoch;
+    int signal_begin;                // this launch announces "my state is complete" (first pass)
+    int signal_end;                  // the last CTA of this launch announces "I am done with your
+                                     // state and your bands hold my slice" (last pass)
+    unsigned int* done_counter;      // CTAs finished so far (self-resetting)
+};
+cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t part_cell0, size_t cell0,
+                                 size_t count, const OutTargets& out, size_t band_stride,
+                                 const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
+                                 const PeerSync& ps);
+
+// Push phase of the peer-memory combine: every record of `state` that belongs to another rank's
+// row slice is stored (posted NVLink writes, no round trip) into that rank's combine buffer, slot
+// `rank`; the touched-tile flags go to every rank's touched staging, slot `rank`.  When
+// `signal` is set the last CTA releases phase 0 ("my contribution has landed") on every rank.
+struct PushTargets {
+    uint32_t* combined[kMaxParts];   // rank k's combine buffer for this pass (kMaxParts slots of max_slice cells)
+    uint32_t* touched_stage[kMaxParts];
+    int rows_per;                    // rows per slice (ceil(height / world))
+    size_t max_slice_cells;
+};
+cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint32_t* touched, int n_tiles,
+                               const GridParams& g, const PassLayout& L, const PushTargets& pt,
+                               const PeerSync& ps, bool push_touched, bool signal);
+
+// store `epoch` into slot (phase, my rank) of every rank's flag array (system-scope release)
+cudaError_t launch_peer_signal(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch);
+// wait until every rank's slot of `phase` in MY flag array has reached `epoch`
+cudaError_t launch_peer_wait(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch);
+// wait (phase 0), then OR the touched-tile flags of all ranks into `merged`
+cudaError_t launch_peer_wait_merge_touched(cudaStream_t s, const PeerFlags& pf, uint32_t epoch,
+                                           const PeerTouched& pt, uint32_t* merged, int n_tiles);
 
 }  // namespace pcrb

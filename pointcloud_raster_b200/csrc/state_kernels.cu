@@ -10,6 +10,8 @@
 // apply the touched-tile NaN rule, write band-major float32 rasters.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace pcrb {
 
 namespace {
@@ -34,18 +36,20 @@ k_init_state(uint32_t* __restrict__ state, size_t cells, const __grid_constant__
     }
 }
 
+// ld.global.cg: cache at L2 only.  A part may be PEER memory (NVLink): the L1 must not serve a
+// line left over from an earlier finalize of the same addresses.
 template <int W>
 __device__ __forceinline__ void load_record(const uint32_t* __restrict__ base, size_t cell, uint32_t (&r)[8])
 {
-    if constexpr (W == 1) r[0] = base[cell];
-    if constexpr (W == 2) { const uint2 t = reinterpret_cast<const uint2*>(base)[cell]; r[0] = t.x; r[1] = t.y; }
+    if constexpr (W == 1) r[0] = __ldcg(base + cell);
+    if constexpr (W == 2) { const uint2 t = __ldcg(reinterpret_cast<const uint2*>(base) + cell); r[0] = t.x; r[1] = t.y; }
     if constexpr (W == 4) {
-        const uint4 t = reinterpret_cast<const uint4*>(base)[cell];
+        const uint4 t = __ldcg(reinterpret_cast<const uint4*>(base) + cell);
         r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
     }
     if constexpr (W == 8) {
-        const uint4 t = reinterpret_cast<const uint4*>(base)[2 * cell];
-        const uint4 u = reinterpret_cast<const uint4*>(base)[2 * cell + 1];
+        const uint4 t = __ldcg(reinterpret_cast<const uint4*>(base) + 2 * cell);
+        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(base) + 2 * cell + 1);
         r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w; r[4] = u.x; r[5] = u.y; r[6] = u.z; r[7] = u.w;
     }
 }
@@ -53,19 +57,10 @@ __device__ __forceinline__ void load_record(const uint32_t* __restrict__ base, s
 // One thread per cell of [cell0, cell0+count).  parts.part[k] points at the
 // record of cell `part_cell0` of rank k's partial state.
 template <int W>
-__global__ void __launch_bounds__(kThreads)
-k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t cell0, size_t count,
-           float* __restrict__ out, size_t band_stride, const __grid_constant__ GridParams g,
-           const __grid_constant__ PassLayout L, const __grid_constant__ FinalizeProgram fp,
-           const uint32_t* __restrict__ touched)
+__device__ __forceinline__ void finalize_cell(const StateParts& parts, size_t part_cell0, size_t cell,
+                                              const OutTargets& outs, size_t band_stride,
+                                              const PassLayout& L, const FinalizeProgram& fp, bool live)
 {
-    const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
-    if (i >= count) return;
-    const size_t cell = cell0 + i;
-    const int row = static_cast<int>(cell / static_cast<size_t>(g.width));
-    const int col = static_cast<int>(cell - static_cast<size_t>(row) * g.width);
-    const bool live = touched[tile_of(g, col, row)] != 0;   // TileManager::tile_has_state
-
     uint32_t r[8];
     load_record<W>(parts.part[0], cell - part_cell0, r);
     for (int k = 1; k < parts.n; ++k) {                      // Op::merge, fixed rank order
@@ -104,7 +99,155 @@ k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t c
                               o = (m == FLT_MAX) ? nan : m; } break;
             }
         }
-        out[static_cast<size_t>(fp.band[b]) * band_stride + cell] = o;
+        const size_t at = static_cast<size_t>(fp.band[b]) * band_stride + cell;
+        for (int t = 0; t < outs.n; ++t) outs.out[t][at] = o;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t cell0, size_t count,
+           const __grid_constant__ OutTargets outs, size_t band_stride, const __grid_constant__ GridParams g,
+           const __grid_constant__ PassLayout L, const __grid_constant__ FinalizeProgram fp,
+           const uint32_t* __restrict__ touched)
+{
+    const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (i >= count) return;
+    const size_t cell = cell0 + i;
+    const int row = static_cast<int>(cell / static_cast<size_t>(g.width));
+    const int col = static_cast<int>(cell - static_cast<size_t>(row) * g.width);
+    const bool live = touched[tile_of(g, col, row)] != 0;   // TileManager::tile_has_state
+    finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live);
+}
+
+// ---- peer flags: system-scope release/acquire ----
+__device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch);
+
+// Peer-memory finalize: wait + touched-tile OR + merge + finalize + completion signal in ONE
+// launch.  Every CTA waits (polling this rank's own flag array) until all ranks' pushed slices
+// have landed in the local combine buffer, merges them with the local partial state in rank
+// order, finalizes, and stores the bands into this rank's and the peers' arrays (posted NVLink
+// writes); the last CTA to finish releases the "done" flag on every rank.
+
+// Push: thread per cell of the WHOLE grid; cells owned by another rank are copied to that rank.
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+k_push_slices(const uint32_t* __restrict__ state, const uint32_t* __restrict__ touched, int n_tiles,
+              const __grid_constant__ GridParams g, const __grid_constant__ PushTargets pt,
+              const __grid_constant__ PeerSync ps, int push_touched, int signal)
+{
+    const PeerFlags& pf = ps.pf;
+    const size_t cells = static_cast<size_t>(g.width) * g.height;
+    const size_t cell = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (cell < cells) {
+        const int row = static_cast<int>(cell / static_cast<size_t>(g.width));
+        const int owner = row / pt.rows_per;
+        if (owner != pf.rank) {
+            const size_t local = cell - static_cast<size_t>(owner) * pt.rows_per * g.width;
+            uint32_t* dst = pt.combined[owner] + (static_cast<size_t>(pf.rank) * pt.max_slice_cells + local) * W;
+            const uint32_t* src = state + cell * W;
+            if constexpr (W == 1) dst[0] = src[0];
+            if constexpr (W == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+            if constexpr (W == 4) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+            if constexpr (W == 8) {
+                reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
+                reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
+            }
+        }
+    }
+    if (push_touched && blockIdx.x == 0) {
+        for (int t = threadIdx.x; t < n_tiles; t += kThreads) {
+            const uint32_t v = touched[t];
+            for (int k = 0; k < pf.n; ++k) pt.touched_stage[k][static_cast<size_t>(pf.rank) * n_tiles + t] = v;
+        }
+    }
+    if (signal) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int done = atomicAdd(ps.done_counter, 1u);
+            if (done == gridDim.x - 1) {
+                *ps.done_counter = 0;
+                for (int k = 0; k < pf.n; ++k) {
+                    uint32_t* slot = pf.flags[k] + pf.rank;                       // phase 0
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(slot), "r"(ps.epoch) : "memory");
+                }
+            }
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+k_finalize_peer(const __grid_constant__ StateParts parts, size_t part_cell0, size_t cell0, size_t count,
+                const __grid_constant__ OutTargets outs, size_t band_stride,
+                const __grid_constant__ GridParams g, const __grid_constant__ PassLayout L,
+                const __grid_constant__ FinalizeProgram fp, const __grid_constant__ PeerSync ps)
+{
+    const PeerFlags& pf = ps.pf;
+    if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + threadIdx.x, ps.epoch);
+    __syncthreads();
+
+    const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (i < count) {
+        const size_t cell = cell0 + i;
+        const int row = static_cast<int>(cell / static_cast<size_t>(g.width));
+        const int col = static_cast<int>(cell - static_cast<size_t>(row) * g.width);
+        const int t = tile_of(g, col, row);
+        uint32_t live = 0;
+        for (int k = 0; k < ps.pt.n; ++k) live |= __ldcg(ps.pt.touched[k] + t);
+        finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live != 0);
+    }
+
+    if (ps.signal_end) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int done = atomicAdd(ps.done_counter, 1u);
+            if (done == gridDim.x - 1) {
+                *ps.done_counter = 0;
+                for (int k = 0; k < pf.n; ++k) {
+                    uint32_t* slot = pf.flags[k] + kMaxParts + pf.rank;       // phase 1
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(slot), "r"(ps.epoch) : "memory");
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_peer_signal(const __grid_constant__ PeerFlags pf, int phase, uint32_t epoch)
+{
+    const int k = threadIdx.x;
+    if (k >= pf.n) return;
+    __threadfence_system();          // everything this stream did so far is visible before the flag
+    uint32_t* slot = pf.flags[k] + phase * kMaxParts + pf.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(slot), "r"(epoch) : "memory");
+}
+
+__device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch)
+{
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+    } while (static_cast<int32_t>(v - epoch) < 0);
+}
+
+__global__ void k_peer_wait(const __grid_constant__ PeerFlags pf, int phase, uint32_t epoch)
+{
+    const int k = threadIdx.x;
+    if (k < pf.n) wait_flag(pf.flags[pf.rank] + phase * kMaxParts + k, epoch);
+}
+
+__global__ void k_peer_wait_merge_touched(const __grid_constant__ PeerFlags pf, uint32_t epoch,
+                                          const __grid_constant__ PeerTouched pt,
+                                          uint32_t* __restrict__ merged, int n_tiles)
+{
+    if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + threadIdx.x, epoch);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        uint32_t v = 0;
+        for (int k = 0; k < pt.n; ++k) v |= __ldcg(pt.touched[k] + t);
+        merged[t] = v;
     }
 }
 
@@ -133,7 +276,7 @@ cudaError_t launch_init_state(cudaStream_t s, uint32_t* state, size_t cells, con
 }
 
 cudaError_t launch_finalize(cudaStream_t s, const StateParts& parts, size_t part_cell0,
-                            size_t cell0, size_t count, float* out, size_t band_stride,
+                            size_t cell0, size_t count, const OutTargets& out, size_t band_stride,
                             const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
                             const uint32_t* touched)
 {
@@ -146,6 +289,62 @@ cudaError_t launch_finalize(cudaStream_t s, const StateParts& parts, size_t part
     case 8: k_finalize<8><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, touched); break;
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+}  // namespace pcrb
+
+namespace pcrb {
+
+cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint32_t* touched, int n_tiles,
+                               const GridParams& g, const PassLayout& L, const PushTargets& pt,
+                               const PeerSync& ps, bool push_touched, bool signal)
+{
+    const size_t cells = static_cast<size_t>(g.width) * g.height;
+    const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, (cells + kThreads - 1) / kThreads));
+    switch (L.width) {
+    case 1: k_push_slices<1><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
+    case 2: k_push_slices<2><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
+    case 4: k_push_slices<4><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
+    case 8: k_push_slices<8><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t part_cell0, size_t cell0,
+                                 size_t count, const OutTargets& out, size_t band_stride,
+                                 const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
+                                 const PeerSync& ps)
+{
+    // count may be 0 (a rank that owns no rows): the handshake still has to happen
+    const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, (count + kThreads - 1) / kThreads));
+    switch (L.width) {
+    case 1: k_finalize_peer<1><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
+    case 2: k_finalize_peer<2><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
+    case 4: k_finalize_peer<4><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
+    case 8: k_finalize_peer<8><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_signal(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch)
+{
+    k_peer_signal<<<1, 32, 0, s>>>(pf, phase, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch)
+{
+    k_peer_wait<<<1, 32, 0, s>>>(pf, phase, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait_merge_touched(cudaStream_t s, const PeerFlags& pf, uint32_t epoch,
+                                           const PeerTouched& pt, uint32_t* merged, int n_tiles)
+{
+    k_peer_wait_merge_touched<<<1, 256, 0, s>>>(pf, epoch, pt, merged, n_tiles);
     return cudaGetLastError();
 }
 

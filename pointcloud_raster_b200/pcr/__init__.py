@@ -13,7 +13,7 @@ Differences that are part of the contract of the new path:
   * ``gpu_fallback_to_cpu`` is accepted and never honoured.
   * additive ``PipelineConfig`` knobs: ``cuda_device_id``, ``deterministic``,
     ``ring_depth``, ``ring_slot_points``, ``staging_threads``, ``point_kernel``,
-    ``warp_aggregate``, ``async_ingest``.
+    ``warp_aggregate``, ``gaussian_kernel``, ``comm_mode``, ``comm_root_only``, ``async_ingest``.
 """
 from __future__ import annotations
 
@@ -693,6 +693,9 @@ class PipelineConfig:
         self.staging_threads = 0
         self.point_kernel = 0
         self.warp_aggregate = 0
+        self.gaussian_kernel = 0
+        self.comm_mode = 0
+        self.comm_root_only = False
         self.async_ingest = False
 
 
@@ -772,6 +775,9 @@ class Pipeline:
         desc.staging_threads = int(getattr(cfg, "staging_threads", 0))
         desc.point_kernel = int(getattr(cfg, "point_kernel", 0))
         desc.warp_aggregate = int(getattr(cfg, "warp_aggregate", 0))
+        desc.gaussian_kernel = int(getattr(cfg, "gaussian_kernel", 0))
+        desc.comm_mode = int(getattr(cfg, "comm_mode", 0))
+        desc.comm_root_only = int(bool(getattr(cfg, "comm_root_only", False)))
         desc.async_ingest = int(bool(getattr(cfg, "async_ingest", False)))
         h = C.c_void_p()
         rc = lib.pcr_pipeline_create(C.byref(desc), C.byref(h))

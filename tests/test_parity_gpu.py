@@ -225,7 +225,8 @@ def test_line_flip_rate(gpu_pcr, oracle):
     assert flips <= max(2.0, 1e-6 * painted)
 
 
-def test_gaussian_vs_oracle(gpu_pcr, oracle):
+@pytest.mark.parametrize("kernel", [1, 2], ids=["scatter", "gather"])
+def test_gaussian_vs_oracle(gpu_pcr, oracle, kernel):
     gc = make_grid(gpu_pcr, 160, 120, tile=64)
     rng = np.random.default_rng(21)
     n = 6000
@@ -239,7 +240,39 @@ def test_gaussian_vs_oracle(gpu_pcr, oracle):
         specs.append(s)
     specs.append(gpu_pcr.gaussian_splat_spec("value", "sigma", "s2", "rot", default_sigma=2.0, max_radius_cells=10.0))
     specs.append(gpu_pcr.gaussian_splat_spec("value", default_sigma_x=16.0, default_sigma_y=16.0, max_radius_cells=32.0))
-    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], specs, "gaussian", device_weights=True)
+    check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], specs, "gaussian", device_weights=True,
+                    gaussian_kernel=kernel)
+
+
+def test_gaussian_gather_edge_cases(gpu_pcr, oracle):
+    """Gather-specific seams: grid not a multiple of the 32-cell gather tile, reference tiles smaller
+    than / misaligned with gather tiles, points on the max edges (centre cell == width), radius cap
+    < 1, huge cap with small sigma, non-unit cells, several chunks."""
+    rng = np.random.default_rng(33)
+    for (w, h, cell, tile, cap, sig) in [(45, 37, 1.0, 10, 6.0, 1.3), (64, 64, 1.0, 4096, 0.4, 2.0),
+                                         (70, 33, 0.5, 24, 300.0, 0.6), (33, 95, 2.0, 7, 12.0, 9.0)]:
+        gc = make_grid(gpu_pcr, w * cell, h * cell, cell=cell, tile=tile)
+        n = 3000
+        x = rng.uniform(-1, w * cell + 1, n); y = rng.uniform(-1, h * cell + 1, n)
+        x[:40] = w * cell; y[40:80] = 0.0; x[80:90] = 0.0; y[90:100] = h * cell
+        ch = {"value": rng.uniform(-1, 1, n).astype(np.float32)}
+        s1 = gpu_pcr.gaussian_splat_spec("value", default_sigma=sig, max_radius_cells=cap)
+        s2 = gpu_pcr.gaussian_splat_spec("value", default_sigma=sig, max_radius_cells=cap)
+        s2.type = gpu_pcr.ReductionType.Count
+        for knobs in ({"gaussian_kernel": 2}, {"gaussian_kernel": 2, "ring_slot_points": 1024}):
+            check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], [s1, s2], f"gather {w}x{h} cap={cap} {knobs}",
+                            device_weights=True, **knobs)
+
+
+def test_gaussian_gather_is_bit_reproducible(gpu_pcr):
+    gc = make_grid(gpu_pcr, 200, 150, tile=64)
+    rng = np.random.default_rng(5)
+    n = 50_000
+    x, y = rng.uniform(0, 200, n), rng.uniform(0, 150, n)
+    ch = {"value": rng.uniform(0, 1, n).astype(np.float32), "sigma": rng.uniform(0.5, 4, n).astype(np.float32)}
+    s = gpu_pcr.gaussian_splat_spec("value", "sigma", "sigma", max_radius_cells=12.0)
+    runs = [run_product(gpu_pcr, gc, [(x, y, ch)], [s], deterministic=True)[0][0].tobytes() for _ in range(3)]
+    assert runs[0] == runs[1] == runs[2]
 
 
 def test_glyph_with_max_is_not_implemented(gpu_pcr):
