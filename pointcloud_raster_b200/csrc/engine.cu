@@ -265,7 +265,7 @@ Status Engine::init(const pcr_pipeline_desc& d)
     gaussian_variant_ = d.gaussian_kernel;
     comm_mode_ = d.comm_mode;
     gather_root_only_ = d.comm_root_only != 0;
-    slot_points_ = d.ring_slot_points ? static_cast<size_t>(d.ring_slot_points) : (size_t(1) << 20);
+    slot_points_ = d.ring_slot_points ? static_cast<size_t>(d.ring_slot_points) : (size_t(1) << 19);   // measured best, 8 copy threads
     slot_points_ = align_up(slot_points_, 1024);
     const int depth = d.ring_depth > 0 ? d.ring_depth : 3;
     ring_.resize(depth);
@@ -611,9 +611,11 @@ bool Engine::use_gather(const Pass& p) const
     if (p.glyph.type != PCR_GLYPH_GAUSSIAN || !gauss_gather_supported(p.layout)) return false;
     if (gaussian_variant_ == 1) return false;
     if (gaussian_variant_ == 2) return true;
-    // auto: the scatter kernel unless bit-reproducibility was asked for (measured on B200, 5M points,
-    // 1000x1000: sigma=16 gather 59 ms vs scatter 61 ms, sigma=4 gather 18.7 ms vs scatter 12.5 ms)
-    return deterministic_;
+    // auto: the gather needs footprints wide enough to amortise its per-(point,tile) tables.  Measured
+    // on B200, 5M points, 1000x1000 (kernel scope): sigma=16 (r=32) gather 17.3 ms vs scatter 58 ms;
+    // sigma=4 (r=12) 6.9 vs 11.1 ms; below ~r=4 the scatter's few REDs per point win.  The radius cap
+    // is the only bound known at plan time.
+    return deterministic_ || p.glyph.max_radius_cells >= 8.0f;
 }
 
 Status Engine::ensure_gauss_scratch(size_t n, size_t record_bytes)

@@ -65,7 +65,7 @@ def run(impl, n_override=None):
         api = orc.load_reference(gpu=(impl == "ref_gpu"))
         mode = api.ExecutionMode.GPU if impl == "ref_gpu" else api.ExecutionMode.CPU
     out = {}
-    for name in CONFIGS:
+    for name in (os.environ.get("PCR_CONFIGS", ",".join(CONFIGS)).split(",")):
         n = 5_000_000
         if impl == "ref_cpu":
             n = {"point_avg": 5_000_000, "line_hl16": 2_000_000, "gauss_s4": 200_000, "gauss_s16": 20_000}[name]
@@ -79,6 +79,11 @@ def run(impl, n_override=None):
         cfg.state_dir = tmp
         if impl == "ref_gpu":
             cfg.gpu_fallback_to_cpu = False
+        if impl == "ours":
+            cfg.gaussian_kernel = int(os.environ.get("PCR_GAUSS_KERNEL", "0"))
+            cfg.staging_threads = int(os.environ.get("PCR_STAGING_THREADS", "0"))
+            cfg.ring_slot_points = int(os.environ.get("PCR_RING_SLOT", "0"))
+            cfg.ring_depth = int(os.environ.get("PCR_RING_DEPTH", "0"))
         p = api.Pipeline.create(cfg)
         if p is None:
             out[name] = {"error": "create failed"}; continue
