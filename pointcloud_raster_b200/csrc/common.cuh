@@ -30,14 +30,23 @@ struct GridParams {
 // quotient d/cs and the product d*(1/cs) are the same real number, hence the
 // same double: the multiply is then bit-exact and 10x cheaper than DDIV.
 // _rn intrinsics keep ptxas from contracting anything into an FMA.
+// EXACT = both cell sizes are powers of two (compile-time variant without the DDIV path: fewer
+// registers, higher occupancy for the streaming Point kernel).
+template <bool EXACT = false>
 __device__ __forceinline__ bool route_cell(const GridParams& g, double x, double y,
                                            int& col, int& row)
 {
     const bool inside = (x >= g.min_x) && (x <= g.max_x) && (y >= g.min_y) && (y <= g.max_y);
     const double dx = __dsub_rn(x, g.min_x);
     const double dy = __dsub_rn(y, g.max_y);
-    const double qx = g.exact_x ? __dmul_rn(dx, g.inv_csx) : __ddiv_rn(dx, g.csx);
-    const double qy = g.exact_y ? __dmul_rn(dy, g.inv_csy) : __ddiv_rn(dy, g.csy);
+    double qx, qy;
+    if constexpr (EXACT) {
+        qx = __dmul_rn(dx, g.inv_csx);
+        qy = __dmul_rn(dy, g.inv_csy);
+    } else {
+        qx = g.exact_x ? __dmul_rn(dx, g.inv_csx) : __ddiv_rn(dx, g.csx);
+        qy = g.exact_y ? __dmul_rn(dy, g.inv_csy) : __ddiv_rn(dy, g.csy);
+    }
     int c = __double2int_rd(qx);          // floor + convert (cvt.rmi.s32.f64)
     int r = __double2int_rd(qy);
     c = max(0, min(c, g.width - 1));

@@ -88,14 +88,14 @@ __device__ __forceinline__ void aggregate_runs(unsigned heads, int lane, float (
 
 // Shared tail of both variants: given one point per lane (warp-converged call),
 // route it and fold it into the state.
-template <int NADD, int NMAX, int NMIN, bool AGG>
+template <int NADD, int NMAX, int NMIN, bool AGG, bool EXACT>
 __device__ __forceinline__ void fold_point(const GridParams& g, const PassLayout& L,
                                            uint32_t* __restrict__ state,
                                            uint32_t* __restrict__ touched, bool live, double x,
                                            double y, const float (&v)[kMaxChan], bool& any_valid)
 {
     int col = 0, row = 0;
-    const bool ok = live && route_cell(g, x, y, col, row);
+    const bool ok = live && route_cell<EXACT>(g, x, y, col, row);
     const size_t cell = static_cast<size_t>(row) * g.width + col;
 
     float add[kMaxAdd], mx[kMaxExt], mn[kMaxExt];
@@ -134,7 +134,7 @@ __device__ __forceinline__ void fold_point(const GridParams& g, const PassLayout
 // ---------------------------------------------------------------------------
 // POINT_DIRECT
 // ---------------------------------------------------------------------------
-template <int NADD, int NMAX, int NMIN, bool AGG>
+template <int NADD, int NMAX, int NMIN, bool AGG, bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 k_point_direct(const double* __restrict__ xs, const double* __restrict__ ys,
                const __grid_constant__ ChannelPtrs ch, size_t n,
@@ -160,7 +160,7 @@ k_point_direct(const double* __restrict__ xs, const double* __restrict__ ys,
     bool any_valid = false;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
-        fold_point<NADD, NMAX, NMIN, AGG>(g, L, state, touched, live[u], x[u], y[u], v[u], any_valid);
+        fold_point<NADD, NMAX, NMIN, AGG, EXACT>(g, L, state, touched, live[u], x[u], y[u], v[u], any_valid);
 
     if (g.tiles_x * g.tiles_y == 1) {
         if (__any_sync(0xffffffffu, any_valid) && (threadIdx.x & 31) == 0 && touched[0] == 0)
@@ -287,7 +287,7 @@ k_point_tma(const double* __restrict__ xs, const double* __restrict__ ys,
             for (int c = 0; c < kMaxChan; ++c) v[c] = (live && c < n_chan) ? sv[c * kTile + i] : 0.0f;
             const double px = live ? sx[i] : 0.0;
             const double py = live ? sy[i] : 0.0;
-            fold_point<NADD, NMAX, NMIN, AGG>(g, L, state, touched, live, px, py, v, any_valid);
+            fold_point<NADD, NMAX, NMIN, AGG, false>(g, L, state, touched, live, px, py, v, any_valid);
         }
         mbar_arrive(&empty_bar[stage]);
         if (threadIdx.x == 0) {
@@ -335,7 +335,10 @@ cudaError_t launch_shape(cudaStream_t s, int variant, const double* x, const dou
         const size_t rest = n - done;
         const size_t per_block = static_cast<size_t>(kThreads) * kUnroll;
         const unsigned grid = static_cast<unsigned>((rest + per_block - 1) / per_block);
-        k_point_direct<NADD, NMAX, NMIN, AGG><<<grid, kThreads, 0, s>>>(x + done, y + done, ch2, rest, state, g, L, touched);
+        if (g.exact_x && g.exact_y)
+            k_point_direct<NADD, NMAX, NMIN, AGG, true><<<grid, kThreads, 0, s>>>(x + done, y + done, ch2, rest, state, g, L, touched);
+        else
+            k_point_direct<NADD, NMAX, NMIN, AGG, false><<<grid, kThreads, 0, s>>>(x + done, y + done, ch2, rest, state, g, L, touched);
     }
     return cudaGetLastError();
 }
