@@ -137,7 +137,9 @@ def build_pipeline(pcr, device, async_ingest, rank=0, world=1, unique_id=None):
     cfg.point_kernel = int(os.environ.get("PCR_POINT_KERNEL", "0"))
     cfg.warp_aggregate = int(os.environ.get("PCR_WARP_AGG", "0"))
     cfg.comm_mode = int(os.environ.get("PCR_COMM_MODE", "0"))
-    cfg.comm_root_only = bool(int(os.environ.get("PCR_COMM_ROOT_ONLY", "0")))
+    # N>1: the finished raster is assembled on rank 0 (the rank that would write the GeoTIFF);
+    # the other ranks keep only their own row slice.  PCR_COMM_ROOT_ONLY=0 gives every rank all bands.
+    cfg.comm_root_only = bool(int(os.environ.get("PCR_COMM_ROOT_ONLY", "1")))
     p = pcr.Pipeline.create(cfg)
     if p is None:
         raise RuntimeError("Pipeline.create failed (no CPU fallback exists)")
@@ -281,7 +283,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "points_per_gpu": N_POINTS, "grid": [GRID, GRID],
                    "reductions": ["Sum", "Count", "Max"], "glyph": "Point",
                    "l2_policy": f"{N_ROTATE} distinct device clouds rotated (400 MB > L2), no step re-reads a resident input",
-                   "step": "ingest(device cloud) + finalize_device()", "timer": "CUDA events on the pipeline stream, max over ranks",
+                   "step": "ingest(device cloud) + finalize_device()" + (
+                       "; N>1: partial grids merged over NVLink peer memory at every finalize, bands assembled on rank 0" if world > 1 else ""), "timer": "CUDA events on the pipeline stream, max over ranks",
                    "wall_ms_per_step": round(t_wall / K, 5)},
         "clocks": clocks,
         "e2e": {"value": round(total_points / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpts/s",
