@@ -202,6 +202,18 @@ int pcr_pipeline_reset(pcr_pipeline *p);
 /* Block until all device work of this pipeline is complete. */
 int pcr_pipeline_synchronize(pcr_pipeline *p);
 
+/* ---- tile-state checkpoints (.pcrt), SURVEY §8f N2 ------------------------------ */
+/* File format of the reference (src/io/tile_state_io.cpp:14-95): 36-byte packed header
+ * {magic "PCRT", version 1, tile_row, tile_col, cols, rows, state_floats, reduction u8, 7 reserved}
+ * + state_floats * cols * rows float32, band-sequential, one file per reference tile named
+ * tile_RRRR_CCCC.pcrt (tile_state_filename, :197-211).  save writes one file per TOUCHED tile per
+ * reduction — directly into `dir` for a single-reduction pipeline (the reference's layout, so the
+ * files interoperate with the reference's TileManager), into `dir`/band_<k>/ otherwise.  load reads
+ * whatever matching files exist (header dims must match, as tile_manager.cpp:272-302 checks), makes
+ * them the accumulated state of their tiles and marks those tiles touched. */
+int pcr_pipeline_save_state(pcr_pipeline *p, const char *dir);
+int pcr_pipeline_load_state(pcr_pipeline *p, const char *dir);
+
 /* ---- GeoTIFF out (GDAL-free; host only) --------------------------------------- */
 /* write_geotiff, src/io/grid_io.cpp:39-182 (called by Pipeline::finalize when output_path is set,
  * src/engine/pipeline.cpp:1350-1361): Float32 tiled (Big)TIFF, one plane per band, nodata NaN, band

@@ -221,5 +221,40 @@ def main():
          "Point + Line + Gaussian reductions side by side in one pipeline")
 
 
+def pcrt_fixtures():
+    """Reference-written .pcrt tile-state files (the reference flushes every dirty tile to state_dir at
+    finalize, tile_manager.cpp:416-426): one single-reduction pipeline per op, so that one file name per
+    tile is unambiguous.  Stored: inputs, the reference bands, and the raw bytes of every tile file."""
+    import glob
+    import shutil
+    import tempfile
+    ref = orc.load_reference()
+    rng = np.random.default_rng(77)
+    gd = orc.GridDesc(0, 0, 40, 24, tile_width=16, tile_height=16)      # 3 x 2 tiles, clipped edge tiles
+    n = 700
+    x = rng.uniform(0, 30, n); y = rng.uniform(0, 24, n)                 # the east tile column stays untouched
+    v = rng.normal(1, 4, n).astype(np.float32)
+    for name, t in (("sum", SUM), ("max", MAX), ("min", MIN), ("count", COUNT), ("average", AVG), ("wavg", WAVG)):
+        cfg = ref.PipelineConfig()
+        cfg.grid = orc.reference_grid(ref, gd)
+        cfg.reductions = [orc.to_reference_spec(ref, Spec("v", t))]
+        cfg.exec_mode = ref.ExecutionMode.CPU
+        cfg.cpu_threads = 1
+        tmp = tempfile.mkdtemp(prefix="pcr_pcrt_")
+        cfg.state_dir = tmp
+        p = ref.Pipeline.create(cfg)
+        p.ingest(orc.reference_cloud(ref, x, y, {"v": v}))
+        p.finalize()
+        band = np.array(p.result().band_array(0))
+        files = {os.path.basename(f): np.frombuffer(open(f, "rb").read(), np.uint8) for f in sorted(glob.glob(tmp + "/*.pcrt"))}
+        shutil.rmtree(tmp)
+        np.savez_compressed(os.path.join(OUT, f"pcrt_{name}.npz"), grid=np.array([0, 0, 40, 24, 1, -1, 16, 16], np.float64),
+                            x=x, y=y, v=v, rtype=np.array([t]), band=band,
+                            **{"file_" + k[:-5]: b for k, b in files.items()})
+        print(f"pcrt_{name}: {len(files)} tile files")
+
+
 if __name__ == "__main__":
-    main()
+    if "--pcrt-only" not in sys.argv:
+        main()
+    pcrt_fixtures()

@@ -99,6 +99,8 @@ SYMBOLS = [
     ("pcr_pipeline_band_name", C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_size_t]),
     ("pcr_pipeline_stats", C.c_int, [C.c_void_p, C.POINTER(Progress)]),
     ("pcr_pipeline_set_progress_callback", C.c_int, [C.c_void_p, PROGRESS_FN, C.c_void_p]),
+    ("pcr_pipeline_save_state", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("pcr_pipeline_load_state", C.c_int, [C.c_void_p, C.c_char_p]),
     ("pcr_pipeline_reset", C.c_int, [C.c_void_p]),
     ("pcr_pipeline_synchronize", C.c_int, [C.c_void_p]),
     ("pcr_geotiff_write", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(GridDesc),

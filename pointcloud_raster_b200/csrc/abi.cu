@@ -209,6 +209,18 @@ int pcr_pipeline_set_progress_callback(pcr_pipeline* p, pcr_progress_fn fn, void
     return PCR_OK;
 }
 
+int pcr_pipeline_save_state(pcr_pipeline* p, const char* dir)
+{
+    NEED(p);
+    if (!dir || !dir[0]) return fail(PCR_INVALID_ARGUMENT, "pcr_pipeline_save_state: empty directory");
+    return finish(eng(p)->save_state(dir));
+}
+int pcr_pipeline_load_state(pcr_pipeline* p, const char* dir)
+{
+    NEED(p);
+    if (!dir || !dir[0]) return fail(PCR_INVALID_ARGUMENT, "pcr_pipeline_load_state: empty directory");
+    return finish(eng(p)->load_state(dir));
+}
 int pcr_pipeline_reset(pcr_pipeline* p) { NEED(p); return finish(eng(p)->reset()); }
 int pcr_pipeline_synchronize(pcr_pipeline* p) { NEED(p); return finish(eng(p)->synchronize()); }
 

@@ -1,0 +1,173 @@
+// checkpoint.cu — tile-state checkpoints in the reference's .pcrt format (host-side C++).
+//
+// Reference: write_tile_state / read_tile_state / tile_state_filename
+// (src/io/tile_state_io.cpp:14-211) and the reload rule of TileManager::acquire
+// (src/engine/tile_manager.cpp:272-302).  The reference's state is band-sequential float per
+// reduction per tile; ours is one interleaved record per cell shared by the fused reductions, so
+// save/load convert between the two on the host: records are copied D2H once, each reduction's
+// state floats are gathered per tile (max/min words decoded from the ordered-int map) and written;
+// load does the reverse and uploads.
+#include "engine.h"
+
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstring>
+
+namespace pcrb {
+
+#define CU_TRY(expr)                                                                     \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return Status::error(PCR_CUDA_ERROR, std::string("CUDA error: ") +           \
+                                 cudaGetErrorString(_e) + " (" #expr ")");               \
+    } while (0)
+#define ST_TRY(expr) do { Status _s = (expr); if (!_s.ok()) return _s; } while (0)
+
+namespace {
+
+#pragma pack(push, 1)
+struct PcrtHeader {            // 36 bytes, little-endian
+    uint32_t magic;            // "PCRT"
+    uint32_t version;          // 1
+    int32_t tile_row, tile_col, cols, rows, state_floats;
+    uint8_t reduction;
+    uint8_t reserved[7];
+};
+#pragma pack(pop)
+static_assert(sizeof(PcrtHeader) == 36, "pcrt header is 36 bytes");
+constexpr uint32_t kMagic = 0x54524350u;
+
+std::string tile_path(const std::string& dir, int row, int col)
+{
+    char name[64];
+    std::snprintf(name, sizeof name, "tile_%04d_%04d.pcrt", row, col);
+    return (dir.empty() || dir.back() == '/') ? dir + name : dir + "/" + name;
+}
+
+bool make_dir(const std::string& d)
+{
+    struct stat st;
+    if (stat(d.c_str(), &st) == 0) return S_ISDIR(st.st_mode);
+    return mkdir(d.c_str(), 0777) == 0;
+}
+
+}  // namespace
+
+// Which record words hold reduction `band`'s state floats, in the reference's order
+// (Sum: {sum}; Count: {count}; Average/WeightedAverage: {sum, count}; Max/Min: {value}).
+static bool band_words(const Pass& p, int band, int& kind, int& wa, int& wb)
+{
+    for (int i = 0; i < p.fin.n; ++i)
+        if (p.fin.band[i] == band) { kind = p.fin.kind[i]; wa = p.fin.word_a[i]; wb = p.fin.word_b[i]; return true; }
+    return false;
+}
+
+Status Engine::save_state(const std::string& dir)
+{
+    CU_TRY(cudaSetDevice(device_));
+    ST_TRY(synchronize());
+    if (!make_dir(dir)) return Status::error(PCR_IO_ERROR, "failed to create state directory: " + dir);
+    std::vector<uint32_t> touched(std::max(1, n_tiles_));
+    CU_TRY(cudaMemcpy(touched.data(), d_touched_, touched.size() * 4, cudaMemcpyDeviceToHost));
+    const bool single = reductions_.size() == 1;
+    for (Pass& p : passes_) {
+        const int W = p.layout.width;
+        std::vector<uint32_t> rec(cells_ * W);
+        CU_TRY(cudaMemcpy(rec.data(), p.d_state, rec.size() * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < p.fin.n; ++i) {
+            const int band = p.fin.band[i];
+            int kind, wa, wb;
+            band_words(p, band, kind, wa, wb);
+            const int sf = kind == FIN_RATIO ? 2 : 1;
+            const std::string bdir = single ? dir : dir + "/band_" + std::to_string(band);
+            if (!make_dir(bdir)) return Status::error(PCR_IO_ERROR, "failed to create state directory: " + bdir);
+            for (int ty = 0; ty < gp_.tiles_y; ++ty)
+                for (int tx = 0; tx < gp_.tiles_x; ++tx) {
+                    if (!touched[ty * gp_.tiles_x + tx]) continue;
+                    const int c0 = tx * gp_.tile_w, r0 = ty * gp_.tile_h;
+                    const int cols = std::min(gp_.tile_w, gp_.width - c0), rows = std::min(gp_.tile_h, gp_.height - r0);
+                    const size_t tc = static_cast<size_t>(cols) * rows;
+                    std::vector<float> out(tc * sf);
+                    for (int r = 0; r < rows; ++r)
+                        for (int c = 0; c < cols; ++c) {
+                            const uint32_t* q = &rec[(static_cast<size_t>(r0 + r) * gp_.width + c0 + c) * W];
+                            const size_t li = static_cast<size_t>(r) * cols + c;
+                            auto as_f = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+                            if (kind == FIN_MAX || kind == FIN_MIN) out[li] = ordered_f32(static_cast<int32_t>(q[wa]));
+                            else out[li] = as_f(q[wa]);
+                            if (sf == 2) out[tc + li] = as_f(q[wb]);
+                        }
+                    PcrtHeader h{};
+                    h.magic = kMagic; h.version = 1; h.tile_row = ty; h.tile_col = tx; h.cols = cols; h.rows = rows;
+                    h.state_floats = sf; h.reduction = static_cast<uint8_t>(reductions_[band].type);
+                    const std::string path = tile_path(bdir, ty, tx);
+                    FILE* f = std::fopen(path.c_str(), "wb");
+                    if (!f) return Status::error(PCR_IO_ERROR, "failed to open file for writing: " + path);
+                    const bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(out.data(), 4, out.size(), f) == out.size();
+                    if (std::fclose(f) != 0 || !ok) return Status::error(PCR_IO_ERROR, "failed to write state data");
+                }
+        }
+    }
+    return Status::success();
+}
+
+Status Engine::load_state(const std::string& dir)
+{
+    CU_TRY(cudaSetDevice(device_));
+    ST_TRY(synchronize());
+    std::vector<uint32_t> touched(std::max(1, n_tiles_));
+    CU_TRY(cudaMemcpy(touched.data(), d_touched_, touched.size() * 4, cudaMemcpyDeviceToHost));
+    const bool single = reductions_.size() == 1;
+    for (Pass& p : passes_) {
+        const int W = p.layout.width;
+        std::vector<uint32_t> rec(cells_ * W);
+        CU_TRY(cudaMemcpy(rec.data(), p.d_state, rec.size() * 4, cudaMemcpyDeviceToHost));
+        bool changed = false;
+        for (int i = 0; i < p.fin.n; ++i) {
+            const int band = p.fin.band[i];
+            int kind, wa, wb;
+            band_words(p, band, kind, wa, wb);
+            const int sf = kind == FIN_RATIO ? 2 : 1;
+            const std::string bdir = single ? dir : dir + "/band_" + std::to_string(band);
+            for (int ty = 0; ty < gp_.tiles_y; ++ty)
+                for (int tx = 0; tx < gp_.tiles_x; ++tx) {
+                    const std::string path = tile_path(bdir, ty, tx);
+                    FILE* f = std::fopen(path.c_str(), "rb");
+                    if (!f) continue;                                   // no file: the tile keeps its state
+                    const int c0 = tx * gp_.tile_w, r0 = ty * gp_.tile_h;
+                    const int cols = std::min(gp_.tile_w, gp_.width - c0), rows = std::min(gp_.tile_h, gp_.height - r0);
+                    PcrtHeader h{};
+                    const bool hok = std::fread(&h, sizeof h, 1, f) == 1 && h.magic == kMagic && h.version == 1;
+                    // the reference discards files whose dimensions do not match (tile_manager.cpp:283-302)
+                    if (!hok || h.cols != cols || h.rows != rows || h.state_floats != sf || h.tile_row != ty || h.tile_col != tx) {
+                        std::fclose(f);
+                        continue;
+                    }
+                    const size_t tc = static_cast<size_t>(cols) * rows;
+                    std::vector<float> in(tc * sf);
+                    const bool dok = std::fread(in.data(), 4, in.size(), f) == in.size();
+                    std::fclose(f);
+                    if (!dok) return Status::error(PCR_IO_ERROR, "incomplete state data (file truncated?): " + path);
+                    for (int r = 0; r < rows; ++r)
+                        for (int c = 0; c < cols; ++c) {
+                            uint32_t* q = &rec[(static_cast<size_t>(r0 + r) * gp_.width + c0 + c) * W];
+                            const size_t li = static_cast<size_t>(r) * cols + c;
+                            auto as_u = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); return u; };
+                            if (kind == FIN_MAX || kind == FIN_MIN) q[wa] = static_cast<uint32_t>(f32_ordered(in[li]));
+                            else q[wa] = as_u(in[li]);
+                            if (sf == 2) q[wb] = as_u(in[tc + li]);
+                        }
+                    touched[ty * gp_.tiles_x + tx] = 1;
+                    changed = true;
+                }
+        }
+        if (changed) CU_TRY(cudaMemcpy(p.d_state, rec.data(), rec.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CU_TRY(cudaMemcpy(d_touched_, touched.data(), touched.size() * 4, cudaMemcpyHostToDevice));
+    finalized_ = false;
+    return Status::success();
+}
+
+}  // namespace pcrb

@@ -111,6 +111,8 @@ public:
     Status stats(pcr_progress& out);
     void set_progress(pcr_progress_fn fn, void* user) { progress_fn_ = fn; progress_user_ = user; }
     Status reset();
+    Status save_state(const std::string& dir);
+    Status load_state(const std::string& dir);
     Status synchronize();
 
     Status profile_enable(bool on);

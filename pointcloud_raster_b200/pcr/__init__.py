@@ -784,7 +784,19 @@ class Pipeline:
         if rc != 0 or not h.value:
             print(f"Pipeline.create failed: {_lib.last_error()}", file=sys.stderr)
             return None
-        return Pipeline(h, cfg, keep)
+        p = Pipeline(h, cfg, keep)
+        # resume: continue from the tile-state files of an earlier run.  (Upstream `resume` is never
+        # read and ANY matching file in state_dir is silently reloaded, tile_manager.cpp:272-302; here
+        # it takes the explicit flag.)
+        if getattr(cfg, "resume", False) and cfg.state_dir:
+            import os
+            if os.path.isdir(cfg.state_dir):
+                try:
+                    p.load_state(cfg.state_dir)
+                except RuntimeError as e:
+                    print(f"Pipeline.create failed: {e}", file=sys.stderr)
+                    return None
+        return p
 
     def __del__(self):
         try:
@@ -895,6 +907,15 @@ class Pipeline:
     def reset(self):
         check(lib.pcr_pipeline_reset(self._h))
         self._result = None
+
+    def save_state(self, directory):
+        """Write the accumulated state as reference-format .pcrt tile files (one per touched tile per
+        reduction; single-reduction pipelines use the reference's own directory layout)."""
+        check(lib.pcr_pipeline_save_state(self._h, str(directory).encode()))
+
+    def load_state(self, directory):
+        """Make the .pcrt files found in `directory` the accumulated state of their tiles."""
+        check(lib.pcr_pipeline_load_state(self._h, str(directory).encode()))
 
     def synchronize(self):
         check(lib.pcr_pipeline_synchronize(self._h))
