@@ -83,6 +83,18 @@ typedef struct pcr_reduction_desc {
     pcr_glyph_desc glyph;
 } pcr_reduction_desc;
 
+/* pcr::FilterPredicate (include/pcr/engine/filter.h:33-38); CompareOp values of filter.h:20-29.
+ * A point survives iff ALL predicates hold (evaluate_predicate, src/engine/filter.cpp:37-58). */
+enum { PCR_CMP_EQUAL = 0, PCR_CMP_NOT_EQUAL = 1, PCR_CMP_LESS = 2, PCR_CMP_LESS_EQUAL = 3,
+       PCR_CMP_GREATER = 4, PCR_CMP_GREATER_EQUAL = 5, PCR_CMP_IN_SET = 6, PCR_CMP_NOT_IN_SET = 7 };
+typedef struct pcr_filter_predicate {
+    const char  *channel_name;     /* Float32 channel of the cloud */
+    int32_t      op;
+    float        value;            /* scalar comparisons */
+    const float *value_set;        /* InSet / NotInSet */
+    int32_t      value_set_size;
+} pcr_filter_predicate;
+
 /* pcr::PipelineConfig (include/pcr/engine/pipeline.h:49-86), hot-path fields,
  * plus the additive knobs of the new path (all default 0). */
 typedef struct pcr_pipeline_desc {
@@ -105,6 +117,9 @@ typedef struct pcr_pipeline_desc {
                                                        GPU pair has P2P access, else NCCL), 1 = NCCL, 2 = peer */
     int32_t                   comm_root_only;       /* 1 = only rank 0 ends with complete bands (other ranks
                                                        keep their own row slice) */
+    const pcr_filter_predicate *filter;             /* PipelineConfig::filter (N3): evaluated on the device,
+                                                       fused in front of routing; NULL/0 = no filter */
+    int32_t                   num_predicates;
     int32_t                   async_ingest;         /* 1 = device-resident ingests return without a
                                                        stream sync; buffers must stay valid until the
                                                        next finalize / synchronize */

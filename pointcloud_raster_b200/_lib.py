@@ -40,6 +40,11 @@ class ReductionDesc(C.Structure):
                 ("output_band_name", C.c_char_p), ("glyph", GlyphDesc)]
 
 
+class FilterPredicate(C.Structure):
+    _fields_ = [("channel_name", C.c_char_p), ("op", C.c_int32), ("value", C.c_float),
+                ("value_set", C.POINTER(C.c_float)), ("value_set_size", C.c_int32)]
+
+
 class PipelineDesc(C.Structure):
     _fields_ = [("grid", GridDesc), ("reductions", C.POINTER(ReductionDesc)),
                 ("num_reductions", C.c_int32), ("exec_mode", C.c_int32),
@@ -48,6 +53,7 @@ class PipelineDesc(C.Structure):
                 ("ring_slot_points", C.c_uint64), ("staging_threads", C.c_int32),
                 ("point_kernel", C.c_int32), ("warp_aggregate", C.c_int32),
                 ("gaussian_kernel", C.c_int32), ("comm_mode", C.c_int32), ("comm_root_only", C.c_int32),
+                ("filter", C.POINTER(FilterPredicate)), ("num_predicates", C.c_int32),
                 ("async_ingest", C.c_int32)]
 
 

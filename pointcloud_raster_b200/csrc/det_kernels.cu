@@ -19,14 +19,14 @@ namespace {
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads)
-k_det_keys(const double* __restrict__ xs, const double* __restrict__ ys, size_t n,
+k_det_keys(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys, size_t n,
            const __grid_constant__ GridParams g, uint32_t* __restrict__ keys,
            uint32_t* __restrict__ idx, uint32_t* __restrict__ touched)
 {
     const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (i >= n) return;
     int col, row;
-    const bool ok = route_cell(g, xs[i], ys[i], col, row);
+    const bool ok = route_cell(g, xs[i], ys[i], col, row) && (mask == nullptr || mask[i] != 0);
     const uint32_t invalid = static_cast<uint32_t>(static_cast<size_t>(g.width) * g.height);
     keys[i] = ok ? static_cast<uint32_t>(static_cast<size_t>(row) * g.width + col) : invalid;
     idx[i] = static_cast<uint32_t>(i);
@@ -93,11 +93,11 @@ size_t det_sort_temp_bytes(size_t n, int key_bits)
     return bytes;
 }
 
-cudaError_t det_build_keys(cudaStream_t s, const double* x, const double* y, size_t n,
+cudaError_t det_build_keys(cudaStream_t s, const uint8_t* mask, const double* x, const double* y, size_t n,
                            const GridParams& g, uint32_t* keys, uint32_t* idx, uint32_t* touched)
 {
     const unsigned grid = static_cast<unsigned>((n + kThreads - 1) / kThreads);
-    k_det_keys<<<grid, kThreads, 0, s>>>(x, y, n, g, keys, idx, touched);
+    k_det_keys<<<grid, kThreads, 0, s>>>(mask, x, y, n, g, keys, idx, touched);
     return cudaGetLastError();
 }
 

@@ -229,6 +229,7 @@ Status Engine::plan()
         if (p.glyph.type == PCR_GLYPH_LINE) { want(p.glyph.direction_channel); want(p.glyph.half_length_channel); }
         if (p.glyph.type == PCR_GLYPH_GAUSSIAN) { want(p.glyph.sigma_x_channel); want(p.glyph.sigma_y_channel); want(p.glyph.rotation_channel); }
     }
+    for (const FilterPredHost& f : filter_) want(f.channel);
     return Status::success();
 }
 
@@ -308,6 +309,20 @@ Status Engine::init(const pcr_pipeline_desc& d)
         reductions_.push_back(std::move(h));
     }
 
+    if (d.num_predicates < 0 || d.num_predicates > kMaxPredicates || (d.num_predicates > 0 && !d.filter))
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: a filter takes at most 8 predicates");
+    for (int i = 0; i < d.num_predicates; ++i) {
+        FilterPredHost f;
+        f.channel = d.filter[i].channel_name ? d.filter[i].channel_name : "";
+        f.op = d.filter[i].op;
+        f.value = d.filter[i].value;
+        if (f.op < PCR_CMP_EQUAL || f.op > PCR_CMP_NOT_IN_SET)
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: unknown filter comparison");
+        if (d.filter[i].value_set && d.filter[i].value_set_size > 0)
+            f.set.assign(d.filter[i].value_set, d.filter[i].value_set + d.filter[i].value_set_size);
+        filter_.push_back(std::move(f));
+    }
+
     if (grid_.width <= 0 || grid_.height <= 0)
         return Status::error(PCR_INVALID_ARGUMENT, "pipeline: grid dimensions must be positive");
     if (grid_.tile_width <= 0 || grid_.tile_height <= 0)
@@ -367,6 +382,14 @@ Status Engine::alloc_state()
     CU_TRY(cudaMalloc(&d_touched_, std::max(1, n_tiles_) * sizeof(uint32_t)));
     const size_t out_bytes = std::max<size_t>(1, reductions_.size()) * cells_ * sizeof(float);
     CU_TRY(cudaMalloc(&d_out_, out_bytes));
+    if (!filter_.empty()) {
+        std::vector<float> all;
+        for (const FilterPredHost& f : filter_) { filter_set_off_.push_back(all.size()); all.insert(all.end(), f.set.begin(), f.set.end()); }
+        CU_TRY(cudaMalloc(&d_filter_sets_, std::max<size_t>(all.size(), 1) * sizeof(float)));
+        if (!all.empty()) CU_TRY(cudaMemcpy(d_filter_sets_, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMalloc(&d_survivors_, sizeof(unsigned long long)));
+        CU_TRY(cudaMemset(d_survivors_, 0, sizeof(unsigned long long)));
+    }
     return Status::success();
 }
 
@@ -384,6 +407,7 @@ Status Engine::reset()
     CU_TRY(cudaSetDevice(device_));
     ST_TRY(synchronize());
     ST_TRY(init_state());
+    if (d_survivors_) CU_TRY(cudaMemsetAsync(d_survivors_, 0, sizeof(unsigned long long), compute_));
     collections_ = 0;
     points_ = 0;
     finalized_ = false;
@@ -411,6 +435,7 @@ Engine::~Engine()
     cudaFree(d_touched_);
     cudaFree(d_touched_all_);
     cudaFree(d_flags_);
+    cudaFree(d_filter_sets_); cudaFree(d_mask_); cudaFree(d_survivors_);
     cudaFree(d_touched_stage_);
     cudaFree(d_out_);
     if (h_out_) cudaFreeHost(h_out_);
@@ -547,6 +572,14 @@ Status Engine::ingest(const double* x, const double* y, size_t n, const pcr_chan
             if (chans[i].name && name == chans[i].name) return &chans[i];
         return nullptr;
     };
+    // filter channels (filter_points_cpu, src/engine/filter.cpp:99-118)
+    for (const FilterPredHost& f : filter_) {
+        const pcr_channel_view* v = find(f.channel);
+        if (!v || !v->data)
+            return Status::error(PCR_INVALID_ARGUMENT, "filter_points: channel not found: " + f.channel);
+        if (v->dtype != PCR_F32)
+            return Status::error(PCR_INVALID_ARGUMENT, "filter_points: only Float32 channels supported for filtering");
+    }
     // value channels must exist and be Float32 (pipeline.cpp:365-378); checked for
     // every reduction BEFORE any work, so a failing ingest leaves the state untouched
     // (the reference would already have folded the reductions listed earlier).
@@ -593,7 +626,8 @@ Status Engine::ingest(const double* x, const double* y, size_t n, const pcr_chan
     else return Status::error(PCR_INVALID_ARGUMENT, "pipeline: unknown memory location");
     ST_TRY(s);
 
-    points_ += n;            // counts every ingested point (pipeline.cpp:749)
+    if (filter_.empty()) points_ += n;   // every ingested point, in-grid or not (pipeline.cpp:749); with a filter
+                                         // the survivors are counted on the device (points_processed += filtered_count)
     ++collections_;
     finalized_ = false;
 
@@ -640,18 +674,49 @@ Status Engine::ensure_gauss_scratch(size_t n, size_t record_bytes)
     return Status::success();
 }
 
+// FilterSpec -> byte mask for this chunk (nullptr when the pipeline has no filter).
+Status Engine::build_mask(size_t n, const std::vector<const float*>& cp, const uint8_t** mask)
+{
+    *mask = nullptr;
+    if (filter_.empty()) return Status::success();
+    if (n > mask_capacity_) {
+        CU_TRY(cudaStreamSynchronize(compute_));
+        cudaFree(d_mask_);
+        d_mask_ = nullptr;
+        mask_capacity_ = 0;
+        const size_t cap = std::max(n, slot_points_);
+        CU_TRY(cudaMalloc(&d_mask_, cap));
+        mask_capacity_ = cap;
+    }
+    FilterProgram fp{};
+    fp.n = static_cast<int>(filter_.size());
+    for (int k = 0; k < fp.n; ++k) {
+        fp.chan[k] = cp[channel_slot(filter_[k].channel)];
+        fp.op[k] = filter_[k].op;
+        fp.value[k] = filter_[k].value;
+        fp.set[k] = d_filter_sets_ + filter_set_off_[k];
+        fp.set_size[k] = static_cast<int>(filter_[k].set.size());
+    }
+    CU_TRY(launch_filter_mask(compute_, fp, n, d_mask_, d_survivors_));
+    ++launches_;
+    *mask = d_mask_;
+    return Status::success();
+}
+
 // Launches every pass over one device-resident chunk on the compute stream.
 Status Engine::run_passes(const double* dx, const double* dy, size_t n,
                           const std::vector<const float*>& cp)
 {
-    if (deterministic_) ST_TRY(run_passes_deterministic(dx, dy, n, cp));
+    const uint8_t* mask = nullptr;
+    ST_TRY(build_mask(n, cp, &mask));
+    if (deterministic_) ST_TRY(run_passes_deterministic(dx, dy, n, cp, mask));
     prof_begin(PROF_ACC, compute_);
     for (Pass& p : passes_) {
         if (deterministic_ && p.glyph.type == PCR_GLYPH_POINT) continue;   // folded by the sort path above
         ChannelPtrs ch{};
         for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])];
         if (p.glyph.type == PCR_GLYPH_POINT) {
-            CU_TRY(launch_point_accumulate(compute_, point_variant_, warp_aggregate_, dx, dy, ch, n,
+            CU_TRY(launch_point_accumulate(compute_, point_variant_, warp_aggregate_, mask, dx, dy, ch, n,
                                            p.d_state, gp_, p.layout, d_touched_, sm_count_));
             ++launches_;
         } else {
@@ -667,7 +732,7 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
             g.rotation = opt(p.glyph.rotation_channel);       g.default_rotation = p.glyph.default_rotation;
             g.max_radius_cells = p.glyph.max_radius_cells;
             if (p.glyph.type == PCR_GLYPH_LINE)
-                CU_TRY(launch_line_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
+                CU_TRY(launch_line_accumulate(compute_, mask, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
             else if (use_gather(p)) {
                 // bounded sub-chunks keep the sort / record scratch small
                 const size_t kSub = size_t(1) << 22;
@@ -680,12 +745,12 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
                     if (g2.sigma_x) g2.sigma_x += q0;
                     if (g2.sigma_y) g2.sigma_y += q0;
                     if (g2.rotation) g2.rotation += q0;
-                    CU_TRY(launch_gaussian_gather(compute_, dx + q0, dy + q0, c2, g2, cnt, p.d_state, gp_, p.layout,
+                    CU_TRY(launch_gaussian_gather(compute_, mask ? mask + q0 : nullptr, dx + q0, dy + q0, c2, g2, cnt, p.d_state, gp_, p.layout,
                                                   d_touched_, gs_, sm_count_));
                     launches_ += 4;   // keys, sort, records, gather
                 }
             } else
-                CU_TRY(launch_gaussian_accumulate(compute_, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
+                CU_TRY(launch_gaussian_accumulate(compute_, mask, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));
             ++launches_;
         }
     }
@@ -851,6 +916,12 @@ Status Engine::stats(pcr_progress& o)
     o.collections_processed = collections_;
     o.collections_total = 0;
     o.points_processed = points_;
+    if (d_survivors_) {
+        unsigned long long kept = 0;
+        CU_TRY(cudaMemcpyAsync(&kept, d_survivors_, sizeof kept, cudaMemcpyDeviceToHost, compute_));
+        CU_TRY(cudaStreamSynchronize(compute_));
+        o.points_processed += kept;
+    }
     std::vector<uint32_t> t(std::max(1, n_tiles_));
     CU_TRY(cudaMemcpyAsync(t.data(), d_touched_, t.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, compute_));
     CU_TRY(cudaStreamSynchronize(compute_));

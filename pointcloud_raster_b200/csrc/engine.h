@@ -50,6 +50,13 @@ struct ReductionHost {
     bool rejected = false;   // glyph + Max/Min: NotImplemented at ingest (pipeline.cpp:500-508)
 };
 
+struct FilterPredHost {
+    std::string channel;
+    int op = 0;
+    float value = 0.f;
+    std::vector<float> set;
+};
+
 // One fused pass: every reduction in it shares the glyph footprint.
 struct Pass {
     GlyphSpecHost glyph;
@@ -93,7 +100,7 @@ struct GaussScratch {
 bool gauss_gather_supported(const PassLayout& L);
 size_t gauss_record_bytes(const PassLayout& L);
 size_t gauss_sort_temp_bytes(size_t n, const GridParams& g);
-cudaError_t launch_gaussian_gather(cudaStream_t s, const double* x, const double* y, const ChannelPtrs& ch,
+cudaError_t launch_gaussian_gather(cudaStream_t s, const uint8_t* mask, const double* x, const double* y, const ChannelPtrs& ch,
                                    const GlyphParams& gp, size_t n, uint32_t* state, const GridParams& g,
                                    const PassLayout& L, uint32_t* touched, GaussScratch& sc, int sm_count);
 
@@ -133,7 +140,7 @@ private:
     Status run_passes(const double* dx, const double* dy, size_t n,
                       const std::vector<const float*>& chan_ptrs);
     Status run_passes_deterministic(const double* dx, const double* dy, size_t n,
-                                    const std::vector<const float*>& chan_ptrs);
+                                    const std::vector<const float*>& chan_ptrs, const uint8_t* mask);
     Status ingest_device(const double* x, const double* y, size_t n,
                          const std::vector<const float*>& chan_ptrs);
     Status ingest_host(const double* x, const double* y, size_t n,
@@ -165,6 +172,15 @@ private:
     bool warp_aggregate_ = true;
     size_t cells_ = 0;
     int n_tiles_ = 0;
+
+    // ---- point filter (FilterSpec) ----
+    std::vector<FilterPredHost> filter_;
+    float* d_filter_sets_ = nullptr;            // all InSet value lists, concatenated
+    std::vector<size_t> filter_set_off_;
+    uint8_t* d_mask_ = nullptr;
+    size_t mask_capacity_ = 0;
+    unsigned long long* d_survivors_ = nullptr; // running count of points that passed the filter
+    Status build_mask(size_t n, const std::vector<const float*>& chan_ptrs, const uint8_t** mask);
 
     // ---- plan / state ----
     std::vector<Pass> passes_;
@@ -239,7 +255,7 @@ private:
 
 // deterministic path (det_kernels.cu)
 size_t det_sort_temp_bytes(size_t n, int key_bits);
-cudaError_t det_build_keys(cudaStream_t s, const double* x, const double* y, size_t n,
+cudaError_t det_build_keys(cudaStream_t s, const uint8_t* mask, const double* x, const double* y, size_t n,
                            const GridParams& g, uint32_t* keys, uint32_t* idx, uint32_t* touched);
 cudaError_t det_sort(cudaStream_t s, void* tmp, size_t tmp_bytes, uint32_t*& keys, uint32_t*& keys_alt,
                      uint32_t*& idx, uint32_t*& idx_alt, size_t n, int key_bits);

@@ -50,7 +50,7 @@ Status Engine::ensure_sort_scratch(size_t n)
 }
 
 Status Engine::run_passes_deterministic(const double* dx, const double* dy, size_t n,
-                                        const std::vector<const float*>& cp)
+                                        const std::vector<const float*>& cp, const uint8_t* mask)
 {
     // point indices are u32 payloads: split very large device clouds
     const size_t kMaxChunk = size_t(1) << 30;
@@ -59,7 +59,7 @@ Status Engine::run_passes_deterministic(const double* dx, const double* dy, size
         ST_TRY(ensure_sort_scratch(cnt));
         const int key_bits = bits_for(cells_);   // keys are cell ids, `cells_` marks invalid points
         prof_begin(PROF_SORT, compute_);
-        CU_TRY(det_build_keys(compute_, dx + p0, dy + p0, cnt, gp_, d_keys_, d_idx_, d_touched_));
+        CU_TRY(det_build_keys(compute_, mask ? mask + p0 : nullptr, dx + p0, dy + p0, cnt, gp_, d_keys_, d_idx_, d_touched_));
         CU_TRY(det_sort(compute_, d_sort_tmp_, sort_tmp_bytes_, d_keys_, d_keys_alt_, d_idx_, d_idx_alt_,
                         cnt, key_bits));
         prof_end(compute_);

@@ -74,13 +74,13 @@ __device__ __forceinline__ void mark_touched(const GridParams& g, uint32_t* touc
 // ---------------------------------------------------------------------------
 template <int NADD>
 __global__ void __launch_bounds__(kThreads)
-k_line(const double* __restrict__ xs, const double* __restrict__ ys,
+k_line(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
        const __grid_constant__ ChannelPtrs ch, const __grid_constant__ GlyphParams gp, size_t n,
        uint32_t* __restrict__ state, const __grid_constant__ GridParams g,
        const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched)
 {
     const size_t p = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
-    if (p >= n) return;
+    if (p >= n || (mask != nullptr && mask[p] == 0)) return;
     const double wx = xs[p], wy = ys[p];
     int col, row;
     if (!route_cell(g, wx, wy, col, row)) return;
@@ -127,7 +127,7 @@ k_line(const double* __restrict__ xs, const double* __restrict__ ys,
 // ---------------------------------------------------------------------------
 template <int NADD>
 __global__ void __launch_bounds__(kThreads)
-k_gaussian_warp(const double* __restrict__ xs, const double* __restrict__ ys,
+k_gaussian_warp(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
                 const __grid_constant__ ChannelPtrs ch, const __grid_constant__ GlyphParams gp,
                 size_t n, uint32_t* __restrict__ state, const __grid_constant__ GridParams g,
                 const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched)
@@ -136,6 +136,7 @@ k_gaussian_warp(const double* __restrict__ xs, const double* __restrict__ ys,
     const size_t warps_total = static_cast<size_t>(gridDim.x) * (kThreads / 32);
     for (size_t p = static_cast<size_t>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5); p < n;
          p += warps_total) {
+        if (mask != nullptr && mask[p] == 0) continue;      // warp-uniform
         const double wx = xs[p], wy = ys[p];
         int col, row;
         if (!route_cell(g, wx, wy, col, row)) continue;     // warp-uniform
@@ -205,7 +206,7 @@ cudaError_t dispatch_nadd(int n_add, F&& f)
 
 }  // namespace
 
-cudaError_t launch_line_accumulate(cudaStream_t s, const double* x, const double* y,
+cudaError_t launch_line_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                    const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                    uint32_t* state, const GridParams& g, const PassLayout& L,
                                    uint32_t* touched)
@@ -213,12 +214,12 @@ cudaError_t launch_line_accumulate(cudaStream_t s, const double* x, const double
     if (n == 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>((n + kThreads - 1) / kThreads);
     return dispatch_nadd(L.n_add, [&](auto na) {
-        k_line<decltype(na)::value><<<grid, kThreads, 0, s>>>(x, y, ch, gp, n, state, g, L, touched);
+        k_line<decltype(na)::value><<<grid, kThreads, 0, s>>>(mask, x, y, ch, gp, n, state, g, L, touched);
         return cudaGetLastError();
     });
 }
 
-cudaError_t launch_gaussian_accumulate(cudaStream_t s, const double* x, const double* y,
+cudaError_t launch_gaussian_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                        const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                        uint32_t* state, const GridParams& g, const PassLayout& L,
                                        uint32_t* touched)
@@ -229,7 +230,7 @@ cudaError_t launch_gaussian_accumulate(cudaStream_t s, const double* x, const do
     if (blocks > 148 * 64) blocks = 148 * 64;
     return dispatch_nadd(L.n_add, [&](auto na) {
         k_gaussian_warp<decltype(na)::value><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(
-            x, y, ch, gp, n, state, g, L, touched);
+            mask, x, y, ch, gp, n, state, g, L, touched);
         return cudaGetLastError();
     });
 }

@@ -34,25 +34,40 @@ struct OutTargets {
 
 enum PointKernelVariant { POINT_DIRECT = 1, POINT_TMA = 2 };
 
+// Point filter (FilterSpec, include/pcr/engine/filter.h:33-51): AND of up to kMaxPredicates
+// comparisons on f32 channels, evaluated into a byte mask (1 = keep) in front of routing.
+constexpr int kMaxPredicates = 8;
+struct FilterProgram {
+    int n;
+    const float* chan[kMaxPredicates];      // channel arrays of the current chunk
+    int op[kMaxPredicates];
+    float value[kMaxPredicates];
+    const float* set[kMaxPredicates];       // device arrays for InSet / NotInSet
+    int set_size[kMaxPredicates];
+};
+// mask[i] = all predicates hold for point i; *survivors += number of kept points
+cudaError_t launch_filter_mask(cudaStream_t s, const FilterProgram& fp, size_t n, uint8_t* mask,
+                               unsigned long long* survivors);
+
 // state identity fill (init_state_kernel<Op>, src/engine/grid_merge.cu:16-23)
 cudaError_t launch_init_state(cudaStream_t s, uint32_t* state, size_t cells, const PassLayout& L);
 
 // Point glyph: fused route + accumulate for every reduction of the pass
 // (kernel_assign + kernel_accumulate_*, tile_router_kernels.cu:34-61,
 //  accumulator_kernels.cu:31-133 — with the CPU routing rule).
-cudaError_t launch_point_accumulate(cudaStream_t s, int variant, bool warp_aggregate,
+cudaError_t launch_point_accumulate(cudaStream_t s, int variant, bool warp_aggregate, const uint8_t* mask,
                                     const double* x, const double* y, const ChannelPtrs& ch,
                                     size_t n, uint32_t* state, const GridParams& g,
                                     const PassLayout& L, uint32_t* touched, int sm_count);
 
 // Line glyph (accumulate_glyph_line_cpu, src/engine/glyph_kernels.cu:188-281)
-cudaError_t launch_line_accumulate(cudaStream_t s, const double* x, const double* y,
+cudaError_t launch_line_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                    const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                    uint32_t* state, const GridParams& g, const PassLayout& L,
                                    uint32_t* touched);
 
 // Gaussian glyph (accumulate_glyph_gaussian_cpu, src/engine/glyph_kernels.cu:79-183)
-cudaError_t launch_gaussian_accumulate(cudaStream_t s, const double* x, const double* y,
+cudaError_t launch_gaussian_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                        const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                        uint32_t* state, const GridParams& g, const PassLayout& L,
                                        uint32_t* touched);

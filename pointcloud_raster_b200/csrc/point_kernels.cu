@@ -136,7 +136,7 @@ __device__ __forceinline__ void fold_point(const GridParams& g, const PassLayout
 // ---------------------------------------------------------------------------
 template <int NADD, int NMAX, int NMIN, bool AGG, bool EXACT>
 __global__ void __launch_bounds__(kThreads)
-k_point_direct(const double* __restrict__ xs, const double* __restrict__ ys,
+k_point_direct(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
                const __grid_constant__ ChannelPtrs ch, size_t n,
                uint32_t* __restrict__ state, const __grid_constant__ GridParams g,
                const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched)
@@ -149,7 +149,7 @@ k_point_direct(const double* __restrict__ xs, const double* __restrict__ ys,
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
         const size_t i = base + static_cast<size_t>(u) * kThreads;
-        live[u] = i < n;
+        live[u] = i < n && (mask == nullptr || mask[i] != 0);
         x[u] = live[u] ? ldg_stream_d(xs + i) : 0.0;
         y[u] = live[u] ? ldg_stream_d(ys + i) : 0.0;
 #pragma unroll
@@ -228,7 +228,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 // arrays 16-byte aligned; the launcher peels the remainder off to POINT_DIRECT.
 template <int NADD, int NMAX, int NMIN, bool AGG>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-k_point_tma(const double* __restrict__ xs, const double* __restrict__ ys,
+k_point_tma(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
             const __grid_constant__ ChannelPtrs ch, size_t n, uint32_t* __restrict__ state,
             const __grid_constant__ GridParams g, const __grid_constant__ PassLayout L,
             uint32_t* __restrict__ touched)
@@ -281,7 +281,7 @@ k_point_tma(const double* __restrict__ xs, const double* __restrict__ ys,
 #pragma unroll
         for (int k = 0; k < kTile / kTmaThreads; ++k) {
             const int i = threadIdx.x + k * kTmaThreads;
-            const bool live = i < cnt;
+            const bool live = i < cnt && (mask == nullptr || mask[p0 + i] != 0);
             float v[kMaxChan];
 #pragma unroll
             for (int c = 0; c < kMaxChan; ++c) v[c] = (live && c < n_chan) ? sv[c * kTile + i] : 0.0f;
@@ -308,7 +308,7 @@ k_point_tma(const double* __restrict__ xs, const double* __restrict__ ys,
 }
 
 template <int NADD, int NMAX, int NMIN, bool AGG>
-cudaError_t launch_shape(cudaStream_t s, int variant, const double* x, const double* y,
+cudaError_t launch_shape(cudaStream_t s, int variant, const uint8_t* mask, const double* x, const double* y,
                          const ChannelPtrs& ch, size_t n, uint32_t* state, const GridParams& g,
                          const PassLayout& L, uint32_t* touched, int sm_count)
 {
@@ -326,7 +326,7 @@ cudaError_t launch_shape(cudaStream_t s, int variant, const double* x, const dou
         const size_t n_main = n & ~static_cast<size_t>(3);
         const size_t n_tiles = (n_main + kTile - 1) / kTile;
         const unsigned grid = static_cast<unsigned>(n_tiles < static_cast<size_t>(sm_count) ? n_tiles : sm_count);
-        kern<<<grid, kTmaThreads, smem, s>>>(x, y, ch, n_main, state, g, L, touched);
+        kern<<<grid, kTmaThreads, smem, s>>>(mask, x, y, ch, n_main, state, g, L, touched);
         done = n_main;
     }
     if (done < n) {
@@ -336,65 +336,65 @@ cudaError_t launch_shape(cudaStream_t s, int variant, const double* x, const dou
         const size_t per_block = static_cast<size_t>(kThreads) * kUnroll;
         const unsigned grid = static_cast<unsigned>((rest + per_block - 1) / per_block);
         if (g.exact_x && g.exact_y)
-            k_point_direct<NADD, NMAX, NMIN, AGG, true><<<grid, kThreads, 0, s>>>(x + done, y + done, ch2, rest, state, g, L, touched);
+            k_point_direct<NADD, NMAX, NMIN, AGG, true><<<grid, kThreads, 0, s>>>(mask ? mask + done : nullptr, x + done, y + done, ch2, rest, state, g, L, touched);
         else
-            k_point_direct<NADD, NMAX, NMIN, AGG, false><<<grid, kThreads, 0, s>>>(x + done, y + done, ch2, rest, state, g, L, touched);
+            k_point_direct<NADD, NMAX, NMIN, AGG, false><<<grid, kThreads, 0, s>>>(mask ? mask + done : nullptr, x + done, y + done, ch2, rest, state, g, L, touched);
     }
     return cudaGetLastError();
 }
 
 template <int NADD, int NMAX, bool AGG>
-cudaError_t dispatch_min(int n_min, cudaStream_t s, int variant, const double* x, const double* y,
+cudaError_t dispatch_min(int n_min, cudaStream_t s, int variant, const uint8_t* mask, const double* x, const double* y,
                          const ChannelPtrs& ch, size_t n, uint32_t* state, const GridParams& g,
                          const PassLayout& L, uint32_t* touched, int sm)
 {
     switch (n_min) {
-    case 0: if constexpr (NADD + NMAX > 0) return launch_shape<NADD, NMAX, 0, AGG>(s, variant, x, y, ch, n, state, g, L, touched, sm);
+    case 0: if constexpr (NADD + NMAX > 0) return launch_shape<NADD, NMAX, 0, AGG>(s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
             else return cudaErrorInvalidValue;
-    case 1: return launch_shape<NADD, NMAX, 1, AGG>(s, variant, x, y, ch, n, state, g, L, touched, sm);
-    case 2: return launch_shape<NADD, NMAX, 2, AGG>(s, variant, x, y, ch, n, state, g, L, touched, sm);
+    case 1: return launch_shape<NADD, NMAX, 1, AGG>(s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
+    case 2: return launch_shape<NADD, NMAX, 2, AGG>(s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
     }
     return cudaErrorInvalidValue;
 }
 
 template <int NADD, bool AGG>
-cudaError_t dispatch_max(int n_max, int n_min, cudaStream_t s, int variant, const double* x,
+cudaError_t dispatch_max(int n_max, int n_min, cudaStream_t s, int variant, const uint8_t* mask, const double* x,
                          const double* y, const ChannelPtrs& ch, size_t n, uint32_t* state,
                          const GridParams& g, const PassLayout& L, uint32_t* touched, int sm)
 {
     switch (n_max) {
-    case 0: return dispatch_min<NADD, 0, AGG>(n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
-    case 1: return dispatch_min<NADD, 1, AGG>(n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
-    case 2: return dispatch_min<NADD, 2, AGG>(n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
+    case 0: return dispatch_min<NADD, 0, AGG>(n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
+    case 1: return dispatch_min<NADD, 1, AGG>(n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
+    case 2: return dispatch_min<NADD, 2, AGG>(n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
     }
     return cudaErrorInvalidValue;
 }
 
 template <bool AGG>
-cudaError_t dispatch_add(cudaStream_t s, int variant, const double* x, const double* y,
+cudaError_t dispatch_add(cudaStream_t s, int variant, const uint8_t* mask, const double* x, const double* y,
                          const ChannelPtrs& ch, size_t n, uint32_t* state, const GridParams& g,
                          const PassLayout& L, uint32_t* touched, int sm)
 {
     switch (L.n_add) {
-    case 0: return dispatch_max<0, AGG>(L.n_max, L.n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
-    case 1: return dispatch_max<1, AGG>(L.n_max, L.n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
-    case 2: return dispatch_max<2, AGG>(L.n_max, L.n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
-    case 3: return dispatch_max<3, AGG>(L.n_max, L.n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
-    case 4: return dispatch_max<4, AGG>(L.n_max, L.n_min, s, variant, x, y, ch, n, state, g, L, touched, sm);
+    case 0: return dispatch_max<0, AGG>(L.n_max, L.n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
+    case 1: return dispatch_max<1, AGG>(L.n_max, L.n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
+    case 2: return dispatch_max<2, AGG>(L.n_max, L.n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
+    case 3: return dispatch_max<3, AGG>(L.n_max, L.n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
+    case 4: return dispatch_max<4, AGG>(L.n_max, L.n_min, s, variant, mask, x, y, ch, n, state, g, L, touched, sm);
     }
     return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
-cudaError_t launch_point_accumulate(cudaStream_t s, int variant, bool warp_aggregate,
+cudaError_t launch_point_accumulate(cudaStream_t s, int variant, bool warp_aggregate, const uint8_t* mask,
                                     const double* x, const double* y, const ChannelPtrs& ch,
                                     size_t n, uint32_t* state, const GridParams& g,
                                     const PassLayout& L, uint32_t* touched, int sm_count)
 {
     if (n == 0) return cudaSuccess;
-    return warp_aggregate ? dispatch_add<true>(s, variant, x, y, ch, n, state, g, L, touched, sm_count)
-                          : dispatch_add<false>(s, variant, x, y, ch, n, state, g, L, touched, sm_count);
+    return warp_aggregate ? dispatch_add<true>(s, variant, mask, x, y, ch, n, state, g, L, touched, sm_count)
+                          : dispatch_add<false>(s, variant, mask, x, y, ch, n, state, g, L, touched, sm_count);
 }
 
 }  // namespace pcrb

@@ -120,6 +120,36 @@ k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t c
     finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live);
 }
 
+// Point filter -> byte mask (evaluate_predicate, src/engine/filter.cpp:37-58; predicates are AND-ed)
+__global__ void __launch_bounds__(kThreads)
+k_filter_mask(const __grid_constant__ FilterProgram fp, size_t n, uint8_t* __restrict__ mask,
+              unsigned long long* __restrict__ survivors)
+{
+    const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+    bool keep = i < n;
+    for (int k = 0; k < fp.n && keep; ++k) {
+        const float v = fp.chan[k][i];
+        bool in_set = false;
+        switch (fp.op[k]) {
+        case 0: keep = v == fp.value[k]; break;
+        case 1: keep = v != fp.value[k]; break;
+        case 2: keep = v <  fp.value[k]; break;
+        case 3: keep = v <= fp.value[k]; break;
+        case 4: keep = v >  fp.value[k]; break;
+        case 5: keep = v >= fp.value[k]; break;
+        case 6:
+        case 7:
+            for (int j = 0; j < fp.set_size[k]; ++j) in_set = in_set || (fp.set[k][j] == v);
+            keep = (fp.op[k] == 6) ? in_set : !in_set;
+            break;
+        default: keep = false;
+        }
+    }
+    if (i < n) mask[i] = keep ? 1 : 0;
+    const unsigned kept = __popc(__ballot_sync(0xffffffffu, keep));
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(survivors, static_cast<unsigned long long>(kept));
+}
+
 // ---- peer flags: system-scope release/acquire ----
 __device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch);
 
@@ -295,6 +325,15 @@ cudaError_t launch_finalize(cudaStream_t s, const StateParts& parts, size_t part
 }  // namespace pcrb
 
 namespace pcrb {
+
+cudaError_t launch_filter_mask(cudaStream_t s, const FilterProgram& fp, size_t n, uint8_t* mask,
+                               unsigned long long* survivors)
+{
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = static_cast<unsigned>((n + kThreads - 1) / kThreads);
+    k_filter_mask<<<grid, kThreads, 0, s>>>(fp, n, mask, survivors);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint32_t* touched, int n_tiles,
                                const GridParams& g, const PassLayout& L, const PushTargets& pt,

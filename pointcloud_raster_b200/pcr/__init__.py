@@ -603,7 +603,7 @@ class PointCloud:
 
 
 # ---------------------------------------------------------------------------
-# Filter (bindings.cpp:397-412) — data classes only; see Pipeline.create
+# Filter (bindings.cpp:397-412); evaluated on the device in front of routing
 # ---------------------------------------------------------------------------
 class FilterPredicate:
     def __init__(self):
@@ -740,11 +740,6 @@ class Pipeline:
     def create(cfg):
         """Returns a Pipeline, or None on failure with the reason on stderr
         (the reference returns nullptr -> None, pipeline.cpp:1294-1304)."""
-        if not cfg.filter.empty():
-            print("Pipeline.create: point filters are not supported on the B200 path "
-                  "(the reference's pipeline filter is itself broken and its test disabled)",
-                  file=sys.stderr)
-            return None
         keep = []
         n = len(cfg.reductions)
         reds = (_lib.ReductionDesc * max(n, 1))()
@@ -779,6 +774,21 @@ class Pipeline:
         desc.comm_mode = int(getattr(cfg, "comm_mode", 0))
         desc.comm_root_only = int(bool(getattr(cfg, "comm_root_only", False)))
         desc.async_ingest = int(bool(getattr(cfg, "async_ingest", False)))
+        preds = list(cfg.filter.predicates)
+        if preds:
+            arr = (_lib.FilterPredicate * len(preds))()
+            for i, fp in enumerate(preds):
+                name = _b(fp.channel_name)
+                vs = (C.c_float * max(len(fp.value_set), 1))(*[float(v) for v in fp.value_set])
+                keep += [name, vs]
+                arr[i].channel_name = name
+                arr[i].op = int(fp.op)
+                arr[i].value = float(fp.value)
+                arr[i].value_set = vs
+                arr[i].value_set_size = len(fp.value_set)
+            keep.append(arr)
+            desc.filter = arr
+            desc.num_predicates = len(preds)
         h = C.c_void_p()
         rc = lib.pcr_pipeline_create(C.byref(desc), C.byref(h))
         if rc != 0 or not h.value:
