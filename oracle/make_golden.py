@@ -254,7 +254,26 @@ def pcrt_fixtures():
         print(f"pcrt_{name}: {len(files)} tile files")
 
 
+def pcrp_fixture():
+    """A PCRP point-cloud file written by the reference's write_point_cloud (point_cloud_io.cpp:74-148)."""
+    import tempfile
+    ref = orc.load_reference()
+    rng = np.random.default_rng(5)
+    n = 37
+    x, y = rng.uniform(0, 100, n), rng.uniform(-50, 50, n)
+    ch = {"intensity": rng.uniform(0, 255, n).astype(np.float32), "z": rng.normal(10, 2, n).astype(np.float32)}
+    c = orc.reference_cloud(ref, x, y, ch)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "cloud.pcr")
+        ref.write_point_cloud(path, c, ref.PointCloudFormat.PCR_Binary)
+        raw = np.frombuffer(open(path, "rb").read(), np.uint8)
+    np.savez_compressed(os.path.join(OUT, "pcrp_reference_file.npz"), raw_file=raw, x=x, y=y, **{"ch_" + k: v for k, v in ch.items()})
+    print(f"pcrp_reference_file: {raw.size} bytes")
+
+
 if __name__ == "__main__":
-    if "--pcrt-only" not in sys.argv:
+    if "--pcrt-only" not in sys.argv and "--io-only" not in sys.argv:
         main()
-    pcrt_fixtures()
+    if "--io-only" not in sys.argv:
+        pcrt_fixtures()
+    pcrp_fixture()

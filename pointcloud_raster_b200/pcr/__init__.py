@@ -1012,16 +1012,22 @@ class PointCloudInfo:
         self.bounds = BBox()
 
 
-def _io_out_of_scope(*_a, **_k):
-    raise RuntimeError("point-cloud file IO (PCRP/CSV/LAS) is outside the B200 hot path; "
-                       "load arrays with numpy and use PointCloud.set_*_array")
+def read_point_cloud(path, format=PointCloudFormat.Auto):
+    from .pointcloud_io import read_point_cloud as _f
+    return _f(path, format)
 
 
-read_point_cloud = write_point_cloud = read_point_cloud_info = _io_out_of_scope
+def write_point_cloud(path, cloud, format=PointCloudFormat.PCR_Binary):
+    from .pointcloud_io import write_point_cloud as _f
+    _f(path, cloud, format)
 
 
-class PointCloudReader:
-    open = staticmethod(_io_out_of_scope)
+def read_point_cloud_info(path, format=PointCloudFormat.Auto):
+    from .pointcloud_io import read_point_cloud_info as _f
+    return _f(path, format)
+
+
+from .pointcloud_io import PointCloudReader  # noqa: E402
 
 
 # ---------------------------------------------------------------------------

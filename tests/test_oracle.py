@@ -15,7 +15,7 @@ from known_answers import ACCUMULATOR, pipeline_cases
 from util import compare_bands
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("pcrt_"))
+                if not os.path.basename(p).startswith(("pcrt_", "pcrp_")))
 
 
 # ---- (a) reference gtest vectors -------------------------------------------------

@@ -23,7 +23,7 @@ from util import (boundary_cloud, clustered_cloud, compare_bands, grid_desc, mak
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("pcrt_"))
+                if not os.path.basename(p).startswith(("pcrt_", "pcrp_")))
 # Line endpoints use f64 cos/sin rounded to f32 where the reference uses glibc cosf/sinf; the two
 # differ in the last bit for a tiny fraction of angles, which can move an endpoint across a .5
 # rounding boundary.  Measured flip rate is reported by test_line_flip_rate; fixtures allow 0.
