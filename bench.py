@@ -116,6 +116,30 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(device):
+    """Best effort: run this rank (and first-touch its pinned staging memory) on the NUMA node the GPU
+    hangs off, so H2D traffic does not cross the socket interconnect.  Returns a short description."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", f"--id={device}", "--query-gpu=pci.bus_id",
+                                       "--format=csv,noheader"], text=True).strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus               # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa: single node"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return f"numa node {node} ({len(ids)} cpus)"
+    except Exception as e:            # noqa
+        return f"numa: unbound ({type(e).__name__})"
+    return "numa: unbound"
+
+
 def build_pipeline(pcr, device, async_ingest, rank=0, world=1, unique_id=None):
     gc = pcr.GridConfig()
     gc.bounds.min_x = gc.bounds.min_y = 0.0
@@ -162,8 +186,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "n/a"
     from pointcloud_raster_b200 import pcr
     if world > 1:
+        import faulthandler           # a rank that dies must not leave the others waiting for ever
+        faulthandler.dump_traceback_later(int(os.environ.get("PCR_BENCH_WATCHDOG", "900")), exit=True)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -285,7 +312,7 @@ def run_ours(args):
                    "l2_policy": f"{N_ROTATE} distinct device clouds rotated (400 MB > L2), no step re-reads a resident input",
                    "step": "ingest(device cloud) + finalize_device()" + (
                        "; N>1: partial grids merged over NVLink peer memory at every finalize, bands assembled on rank 0" if world > 1 else ""), "timer": "CUDA events on the pipeline stream, max over ranks",
-                   "wall_ms_per_step": round(t_wall / K, 5)},
+                   "wall_ms_per_step": round(t_wall / K, 5), "rank0_affinity": numa},
         "clocks": clocks,
         "e2e": {"value": round(total_points / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpts/s",
                 "h2d_bytes_per_step": N_POINTS * BYTES_PER_POINT, "d2h_bytes_per_step": GRID * GRID * 4 * 3,

@@ -417,6 +417,7 @@ Status Engine::reset()
 Status Engine::synchronize()
 {
     CU_TRY(cudaSetDevice(device_));
+    ST_TRY(peer_quiesce());
     CU_TRY(cudaStreamSynchronize(copy_));
     CU_TRY(cudaStreamSynchronize(compute_));
     return Status::success();
@@ -856,6 +857,7 @@ Status Engine::finalize(bool to_host)
     CU_TRY(cudaSetDevice(device_));
     if (world_ > 1) ST_TRY(finalize_multi());
     else ST_TRY(finalize_single());
+    if (to_host || !async_device_ingest_) ST_TRY(peer_quiesce());   // peers' band stores must have landed
     if (to_host) {
         const size_t bytes = reductions_.size() * cells_ * sizeof(float);
         if (!h_out_) CU_TRY(cudaMallocHost(&h_out_, std::max<size_t>(bytes, 4)));

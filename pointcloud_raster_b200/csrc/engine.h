@@ -251,6 +251,8 @@ private:
     PeerBuffers peer_[kMaxParts];
     uint32_t* d_flags_ = nullptr;     // [2 phases][kMaxParts]
     uint32_t epoch_ = 0;
+    uint32_t waited_epoch_ = 0;        // last epoch whose phase-1 ("everyone is done") flags were awaited
+    Status peer_quiesce();            // enqueue that wait if it is still owed
 };
 
 // deterministic path (det_kernels.cu)

@@ -296,8 +296,8 @@ void Engine::peer_unmap()
 //   k_finalize_peer waits until all ranks' pushes have landed here, merges the `world` parts of
 //                   my slice in rank order (Op::merge), finalizes, stores the bands into my array
 //                   and the peers' arrays; the last CTA releases phase 1
-//   k_peer_wait     phase 1 from everyone: my combine buffer, my state and my bands are mine
-//                   again, the next ingest may run.
+//   (k_peer_wait)   phase 1 from everyone is awaited lazily — by the next push kernel, or by
+//                   peer_quiesce() before the host reads the bands; the next ingest does not wait.
 Status Engine::finalize_multi_peer()
 {
     ++epoch_;
@@ -351,8 +351,21 @@ Status Engine::finalize_multi_peer()
         ++launches_;
     }
     prof_end(compute_);
-    CU_TRY(launch_peer_wait(compute_, ps.pf, 1, epoch_));
+    // Not awaited here: the peers' "done" flags of this epoch.  My next ingest only touches my own
+    // state, which no peer reads; the flags are awaited by the next push kernel (before it overwrites
+    // the peers' combine buffers) and by peer_quiesce() before the host looks at the bands.
+    return Status::success();
+}
+
+Status Engine::peer_quiesce()
+{
+    if (!peer_ok_ || waited_epoch_ == epoch_) return Status::success();
+    PeerFlags pf{};
+    pf.n = world_; pf.rank = rank_;
+    for (int k = 0; k < world_; ++k) pf.flags[k] = peer_[k].flags;
+    CU_TRY(launch_peer_wait(compute_, pf, 1, epoch_));
     ++launches_;
+    waited_epoch_ = epoch_;
     return Status::success();
 }
 

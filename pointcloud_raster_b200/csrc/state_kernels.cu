@@ -151,7 +151,13 @@ k_filter_mask(const __grid_constant__ FilterProgram fp, size_t n, uint8_t* __res
 }
 
 // ---- peer flags: system-scope release/acquire ----
-__device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch);
+__device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch)
+{
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+    } while (static_cast<int32_t>(v - epoch) < 0);
+}
 
 // Peer-memory finalize: wait + touched-tile OR + merge + finalize + completion signal in ONE
 // launch.  Every CTA waits (polling this rank's own flag array) until all ranks' pushed slices
@@ -167,6 +173,13 @@ k_push_slices(const uint32_t* __restrict__ state, const uint32_t* __restrict__ t
               const __grid_constant__ PeerSync ps, int push_touched, int signal)
 {
     const PeerFlags& pf = ps.pf;
+    // The peers' combine buffers may still be being read by their previous finalize: wait for
+    // their "done" flags of the previous epoch (phase 1) before overwriting them.  Nothing else
+    // of the previous finalize is waited for here, so the ingest in between ran unhindered.
+    if (ps.epoch > 1) {
+        if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + kMaxParts + threadIdx.x, ps.epoch - 1);
+        __syncthreads();
+    }
     const size_t cells = static_cast<size_t>(g.width) * g.height;
     const size_t cell = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (cell < cells) {
@@ -252,14 +265,6 @@ __global__ void k_peer_signal(const __grid_constant__ PeerFlags pf, int phase, u
     __threadfence_system();          // everything this stream did so far is visible before the flag
     uint32_t* slot = pf.flags[k] + phase * kMaxParts + pf.rank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(slot), "r"(epoch) : "memory");
-}
-
-__device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch)
-{
-    uint32_t v;
-    do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
-    } while (static_cast<int32_t>(v - epoch) < 0);
 }
 
 __global__ void k_peer_wait(const __grid_constant__ PeerFlags pf, int phase, uint32_t epoch)
