@@ -114,9 +114,14 @@ k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t c
     const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (i >= count) return;
     const size_t cell = cell0 + i;
-    const int row = static_cast<int>(cell / static_cast<size_t>(g.width));
-    const int col = static_cast<int>(cell - static_cast<size_t>(row) * g.width);
-    const bool live = touched[tile_of(g, col, row)] != 0;   // TileManager::tile_has_state
+    bool live;                                               // TileManager::tile_has_state
+    if (g.tiles_x * g.tiles_y == 1) {
+        live = touched[0] != 0;
+    } else {                                                 // cells < 2^32 (engine check): 32-bit divides
+        const unsigned row = static_cast<unsigned>(cell) / static_cast<unsigned>(g.width);
+        const unsigned col = static_cast<unsigned>(cell) - row * static_cast<unsigned>(g.width);
+        live = touched[tile_of(g, static_cast<int>(col), static_cast<int>(row))] != 0;
+    }
     finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live);
 }
 
@@ -234,9 +239,9 @@ k_finalize_peer(const __grid_constant__ StateParts parts, size_t part_cell0, siz
     const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (i < count) {
         const size_t cell = cell0 + i;
-        const int row = static_cast<int>(cell / static_cast<size_t>(g.width));
-        const int col = static_cast<int>(cell - static_cast<size_t>(row) * g.width);
-        const int t = tile_of(g, col, row);
+        const unsigned row = static_cast<unsigned>(cell) / static_cast<unsigned>(g.width);
+        const unsigned col = static_cast<unsigned>(cell) - row * static_cast<unsigned>(g.width);
+        const int t = (g.tiles_x * g.tiles_y == 1) ? 0 : tile_of(g, static_cast<int>(col), static_cast<int>(row));
         uint32_t live = 0;
         for (int k = 0; k < ps.pt.n; ++k) live |= __ldcg(ps.pt.touched[k] + t);
         finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live != 0);
