@@ -18,6 +18,7 @@ namespace pcrb {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMaxProfile = 161;      // separable fast path of the Gaussian scatter: footprints up to r = 80
 
 // libstdc++ std::min/std::max (NaN behaviour differs from fminf/fmaxf), as called
 // at glyph_kernels.cu:131,228-229 of the reference.
@@ -132,7 +133,9 @@ k_gaussian_warp(const uint8_t* __restrict__ mask, const double* __restrict__ xs,
                 size_t n, uint32_t* __restrict__ state, const __grid_constant__ GridParams g,
                 const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched)
 {
+    __shared__ float s_profile[kThreads / 32][2][kMaxProfile];     // per warp: wx[], wy[]
     const int lane = threadIdx.x & 31;
+    const bool unrotated = gp.rotation == nullptr && gp.default_rotation == 0.0f;
     const size_t warps_total = static_cast<size_t>(gridDim.x) * (kThreads / 32);
     for (size_t p = static_cast<size_t>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5); p < n;
          p += warps_total) {
@@ -172,6 +175,47 @@ k_gaussian_warp(const uint8_t* __restrict__ mask, const double* __restrict__ xs,
 
         const int side = 2 * r + 1;
         const int total = side * side;
+
+        // Separable fast path.  Without rotation w(dx,dy) = exp(-ax/2 - ay/2) exactly (cos(-0) = 1,
+        // sin(-0) = -0), so w = wx[dx] * wy[dy] up to ~5 ulp; that is only safe where the `w < 1e-6`
+        // cut provably never fires (exponent bound E < 13, i.e. w > 2.2e-6) and the values are finite.
+        // The two 1-D profiles (one IEEE divide + one expf per entry) are built by the warp in shared
+        // memory; the (2r+1)^2 cells then cost two LDS and two multiplies each instead of two divides,
+        // the rotation and an expf.  ncu (profiles/r01_other_kernels_ncu_full.json) showed the plain
+        // per-cell evaluation to be issue-bound (92 % issue slots, L2 atomics 27 %).
+        bool fast = unrotated && side <= kMaxProfile;
+        if (fast) {
+            const float m = static_cast<float>(r + 1);
+            const float ex = m / sx, ey = m / sy;
+            fast = (0.5f * (ex * ex + ey * ey)) < 13.0f;
+#pragma unroll
+            for (int c = 0; c < kMaxChan; ++c) fast = fast && (c >= L.n_chan || fabsf(v[c]) <= 3.0e38f);
+        }
+        if (fast) {
+            float* wxs = s_profile[threadIdx.x >> 5][0];
+            float* wys = s_profile[threadIdx.x >> 5][1];
+            __syncwarp();
+            for (int i = lane; i < side; i += 32) {
+                const float d = static_cast<float>(i - r);
+                const float tx = __fdiv_rn(__fsub_rn(d, subx), sx), ty = __fdiv_rn(__fsub_rn(d, suby), sy);
+                wxs[i] = expf(__fmul_rn(-0.5f, __fmul_rn(tx, tx)));
+                wys[i] = expf(__fmul_rn(-0.5f, __fmul_rn(ty, ty)));
+            }
+            __syncwarp();
+            int dx = -r + lane, dy = -r;
+            while (dx > r) { dx -= side; ++dy; }
+            for (int idx = lane; idx < total; idx += 32) {
+                const int gc = icx + dx, gr = icy + dy;
+                if (gc >= clip.c0 && gc < clip.c1 && gr >= clip.r0 && gr < clip.r1) {
+                    const float w = __fmul_rn(wxs[dx + r], wys[dy + r]);
+                    if (!(w < 1e-6f)) paint<NADD>(state, g, gc, gr, L, v, w);
+                }
+                dx += 32;
+                while (dx > r) { dx -= side; ++dy; }
+            }
+            continue;
+        }
+
         int dx = -r + lane, dy = -r;
         while (dx > r) { dx -= side; ++dy; }
         for (int idx = lane; idx < total; idx += 32) {

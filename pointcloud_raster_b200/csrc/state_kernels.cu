@@ -56,10 +56,14 @@ __device__ __forceinline__ void load_record(const uint32_t* __restrict__ base, s
 
 // One thread per cell of [cell0, cell0+count).  parts.part[k] points at the
 // record of cell `part_cell0` of rank k's partial state.
+// Merged record of one cell -> all bands of the pass.  The record words are parked in shared memory
+// ([word][thread], conflict-free) so that a band picks its words with one LDS at a warp-uniform row
+// instead of a chain of register selects; the band program itself is warp-uniform.
 template <int W>
 __device__ __forceinline__ void finalize_cell(const StateParts& parts, size_t part_cell0, size_t cell,
                                               const OutTargets& outs, size_t band_stride,
-                                              const PassLayout& L, const FinalizeProgram& fp, bool live)
+                                              const PassLayout& L, const FinalizeProgram& fp, bool live,
+                                              uint32_t (*s_words)[kThreads])
 {
     uint32_t r[8];
     load_record<W>(parts.part[0], cell - part_cell0, r);
@@ -76,27 +80,26 @@ __device__ __forceinline__ void finalize_cell(const StateParts& parts, size_t pa
                 r[j] = static_cast<uint32_t>(min(static_cast<int32_t>(r[j]), static_cast<int32_t>(q[j])));
         }
     }
+#pragma unroll
+    for (int j = 0; j < W; ++j) s_words[j][threadIdx.x] = r[j];   // own column only: no sync needed
 
     const float nan = __int_as_float(0x7fc00000);
     for (int b = 0; b < fp.n; ++b) {
         float o = nan;
         if (live) {
-            uint32_t wa = 0, wb = 0;
-#pragma unroll
-            for (int j = 0; j < W; ++j) {           // register select, no local memory
-                if (j == fp.word_a[b]) wa = r[j];
-                if (j == fp.word_b[b]) wb = r[j];
-            }
+            const int kind = fp.kind[b];
+            const uint32_t wa = s_words[fp.word_a[b]][threadIdx.x];
             const float a = __uint_as_float(wa);
-            switch (fp.kind[b]) {
-            case FIN_SUM:   o = a; break;                                           // SumOp::finalize
-            case FIN_COUNT: o = a > 0.0f ? a : nan; break;                          // CountOp::finalize
-            case FIN_RATIO: { const float d = __uint_as_float(wb);                  // Average / WeightedAverage
-                              o = d > 0.0f ? __fdiv_rn(a, d) : nan; } break;
-            case FIN_MAX:   { const float m = ordered_f32(static_cast<int32_t>(wa)); // MaxOp::finalize
-                              o = (m == -FLT_MAX) ? nan : m; } break;
-            case FIN_MIN:   { const float m = ordered_f32(static_cast<int32_t>(wa));
-                              o = (m == FLT_MAX) ? nan : m; } break;
+            if (kind == FIN_SUM) {                                               // SumOp::finalize
+                o = a;
+            } else if (kind == FIN_COUNT) {                                      // CountOp::finalize
+                o = a > 0.0f ? a : nan;
+            } else if (kind == FIN_RATIO) {                                      // Average / WeightedAverage
+                const float d = __uint_as_float(s_words[fp.word_b[b]][threadIdx.x]);
+                o = d > 0.0f ? __fdiv_rn(a, d) : nan;
+            } else {                                                             // MaxOp / MinOp::finalize
+                const float m = ordered_f32(static_cast<int32_t>(wa));
+                o = (m == (kind == FIN_MAX ? -FLT_MAX : FLT_MAX)) ? nan : m;
             }
         }
         const size_t at = static_cast<size_t>(fp.band[b]) * band_stride + cell;
@@ -111,6 +114,7 @@ k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t c
            const __grid_constant__ PassLayout L, const __grid_constant__ FinalizeProgram fp,
            const uint32_t* __restrict__ touched)
 {
+    __shared__ uint32_t s_words[W][kThreads];
     const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (i >= count) return;
     const size_t cell = cell0 + i;
@@ -122,7 +126,7 @@ k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t c
         const unsigned col = static_cast<unsigned>(cell) - row * static_cast<unsigned>(g.width);
         live = touched[tile_of(g, static_cast<int>(col), static_cast<int>(row))] != 0;
     }
-    finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live);
+    finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live, s_words);
 }
 
 // Point filter -> byte mask (evaluate_predicate, src/engine/filter.cpp:37-58; predicates are AND-ed)
@@ -232,6 +236,7 @@ k_finalize_peer(const __grid_constant__ StateParts parts, size_t part_cell0, siz
                 const __grid_constant__ GridParams g, const __grid_constant__ PassLayout L,
                 const __grid_constant__ FinalizeProgram fp, const __grid_constant__ PeerSync ps)
 {
+    __shared__ uint32_t s_words[W][kThreads];
     const PeerFlags& pf = ps.pf;
     if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + threadIdx.x, ps.epoch);
     __syncthreads();
@@ -244,7 +249,7 @@ k_finalize_peer(const __grid_constant__ StateParts parts, size_t part_cell0, siz
         const int t = (g.tiles_x * g.tiles_y == 1) ? 0 : tile_of(g, static_cast<int>(col), static_cast<int>(row));
         uint32_t live = 0;
         for (int k = 0; k < ps.pt.n; ++k) live |= __ldcg(ps.pt.touched[k] + t);
-        finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live != 0);
+        finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live != 0, s_words);
     }
 
     if (ps.signal_end) {

@@ -10,11 +10,14 @@ import glyph_bench as gb
 
 name, n = sys.argv[1], int(sys.argv[2])
 kernel = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+extra = dict(a.split("=") for a in sys.argv[4:])          # e.g. point_kernel=2 deterministic=1
 x, y, ch = gb.arrays(n)
 b = pcr.BBox(); b.min_x = b.min_y = 0.0; b.max_x = b.max_y = float(gb.GRID)
 gc = pcr.GridConfig(); gc.bounds = b; gc.compute_dimensions()
 cfg = pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = [gb.make_spec(pcr, name)]
 cfg.exec_mode = pcr.ExecutionMode.GPU; cfg.gaussian_kernel = kernel
+for k_, v_ in extra.items():
+    setattr(cfg, k_, int(v_))
 p = pcr.Pipeline.create(cfg)
 c = pcr.PointCloud.create(n); c.set_x_array(x); c.set_y_array(y)
 for k, v in ch.items():
@@ -25,4 +28,4 @@ for i in range(3):
     p.profile_reset()
     t0 = time.perf_counter(); p.ingest(d); p.finalize(); dt = time.perf_counter() - t0
     pr = p.profile_read()
-    print(f"{name} n={n} kernel={kernel}: wall {dt*1e3:.3f} ms, accumulate {pr['accumulate_ms']:.3f} ms, finalize {pr['finalize_ms']:.3f} ms")
+    print(f"{name} n={n} kernel={kernel} {extra}: sort {pr['sort_ms']:.3f} ms, wall {dt*1e3:.3f} ms, accumulate {pr['accumulate_ms']:.3f} ms, finalize {pr['finalize_ms']:.3f} ms")
