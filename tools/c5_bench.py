@@ -10,10 +10,13 @@ from pointcloud_raster_b200 import pcr
 W = 20000
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+dist = sys.argv[3] if len(sys.argv) > 3 else "clustered"      # or "uniform": the worst case for record locality
 
 
 def clustered(n, seed):
     rng = np.random.default_rng(seed)
+    if dist == "uniform":
+        return rng.uniform(0, W, n), rng.uniform(0, W, n), rng.uniform(0, 1, n).astype(np.float32)
     K = 64
     cx, cy = rng.uniform(0, W, K), rng.uniform(0, W, K)
     sig = np.exp(rng.uniform(np.log(50), np.log(2000), K))
@@ -46,7 +49,7 @@ for i in range(k):
 p.synchronize()
 dt = time.perf_counter() - t0
 pr = p.profile_read()
-print(f"device-resident ingest: {k} x {n} clustered points on {W}x{W}: {k*n/dt/1e6:.1f} Mpts/s "
+print(f"device-resident ingest: {k} x {n} {dist} points on {W}x{W}: {k*n/dt/1e6:.1f} Mpts/s "
       f"(accumulate {pr['accumulate_ms']/k:.2f} ms per ingest = {n*20/(pr['accumulate_ms']/k*1e-3)/1e9:.1f} GB/s algorithmic)")
 t0 = time.perf_counter(); p.finalize_device(); p.synchronize(); t1 = time.perf_counter() - t0
 t0 = time.perf_counter(); p.finalize(); t2 = time.perf_counter() - t0
@@ -54,4 +57,4 @@ print(f"finalize_device {t1*1e3:.1f} ms, finalize (with D2H of 3 x 1.6 GB bands)
 t0 = time.perf_counter(); p.ingest(clouds[0][1]); p.synchronize(); dt = time.perf_counter() - t0
 print(f"host (pageable) ingest of {n} points: {n/dt/1e6:.1f} Mpts/s")
 cnt = np.asarray(p.result().band_array(2))
-print("count band sum", float(np.nansum(cnt.astype(np.float64))), "expected", (k + 2) * n)
+print("count band sum", float(np.nansum(cnt.astype(np.float64))), "expected", (k + 1) * n)
