@@ -161,6 +161,9 @@ def build_pipeline(pcr, device, async_ingest, rank=0, world=1, unique_id=None):
     cfg.point_kernel = int(os.environ.get("PCR_POINT_KERNEL", "0"))
     cfg.warp_aggregate = int(os.environ.get("PCR_WARP_AGG", "0"))
     cfg.comm_mode = int(os.environ.get("PCR_COMM_MODE", "0"))
+    cfg.ring_slot_points = int(os.environ.get("PCR_RING_SLOT", "0"))
+    cfg.ring_depth = int(os.environ.get("PCR_RING_DEPTH", "0"))
+    cfg.staging_threads = int(os.environ.get("PCR_STAGING_THREADS", "0"))
     # N>1: the finished raster is assembled on rank 0 (the rank that would write the GeoTIFF);
     # the other ranks keep only their own row slice.  PCR_COMM_ROOT_ONLY=0 gives every rank all bands.
     cfg.comm_root_only = bool(int(os.environ.get("PCR_COMM_ROOT_ONLY", "1")))

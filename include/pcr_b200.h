@@ -107,7 +107,8 @@ typedef struct pcr_pipeline_desc {
     /* --- additive knobs --- */
     int32_t                   deterministic;        /* 1 = sort-then-segmented-reduce, bit-reproducible */
     int32_t                   ring_depth;           /* host-ingest staging slots, 0 = default (3) */
-    uint64_t                  ring_slot_points;     /* points per slot, 0 = default (512 Ki) */
+    uint64_t                  ring_slot_points;     /* points per ring chunk, 0 = default (256 Ki staged
+                                                       from pageable memory, 2 Mi direct from pinned) */
     int32_t                   staging_threads;      /* host copy threads, 0 = default */
     int32_t                   point_kernel;         /* 0 = auto, 1 = direct LDG, 2 = TMA-staged persistent */
     int32_t                   warp_aggregate;       /* 0 = auto (adaptive run aggregation), 2 = off */

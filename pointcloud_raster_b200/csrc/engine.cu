@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <emmintrin.h>
 
 namespace pcrb {
 
@@ -28,11 +29,36 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ---------------------------------------------------------------------------
 // CopyPool
 // ---------------------------------------------------------------------------
+// Staging copy pageable -> pinned.  The pinned slot is only ever read by the DMA
+// engine, so it is written with non-temporal stores: no read-for-ownership of
+// the destination lines and no cache pollution (3 instead of 4 DRAM transfers per
+// staged byte, counting the DMA read).  Measured on the B200 host (16 cores), API scope,
+// 5M-point Point Average: 1.49 -> 1.95 Gpts/s with 8 copy threads, 2.04 with 12.
+void CopyPool::stage_copy(void* dst, const void* src, size_t bytes)
+{
+    if (bytes < 4096) { std::memcpy(dst, src, bytes); return; }
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+    if (head) { std::memcpy(d, s, head); d += head; s += head; bytes -= head; }
+    const size_t body = bytes & ~size_t(63);
+    for (size_t i = 0; i < body; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
+        const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+    }
+    _mm_sfence();
+    if (bytes > body) std::memcpy(d + body, s + body, bytes - body);
+}
+
 CopyPool::CopyPool(int threads)
 {
-    const int extra = std::max(0, threads - 1);
-    jobs_.resize(extra);
-    for (int i = 0; i < extra; ++i) workers_.emplace_back(&CopyPool::worker, this, i);
+    for (int i = 0; i < std::max(0, threads); ++i) workers_.emplace_back(&CopyPool::worker, this);
 }
 
 CopyPool::~CopyPool()
@@ -46,48 +72,81 @@ CopyPool::~CopyPool()
     for (auto& t : workers_) t.join();
 }
 
-void CopyPool::worker(int idx)
+void CopyPool::worker()
 {
     uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
-        Job job;
-        {
-            std::unique_lock<std::mutex> lk(mu_);
-            cv_start_.wait(lk, [&] { return generation_ != seen; });
-            seen = generation_;
-            if (stop_) return;
-            job = jobs_[idx];
-        }
-        if (job.bytes) std::memcpy(job.dst, job.src, job.bytes);
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--pending_ == 0) cv_done_.notify_one();
-        }
+        cv_start_.wait(lk, [&] { return stop_ || (job_open_ && generation_ != seen); });
+        if (stop_) return;
+        seen = generation_;
+        ++active_;                       // joined this job; end() waits for us
+        lk.unlock();
+        drain(true);
+        lk.lock();
+        if (--active_ == 0) cv_done_.notify_all();
     }
 }
 
-void CopyPool::copy(void* dst, const void* src, size_t bytes)
+// Pull pieces from the cursor.  A piece whose chunk is not writable yet (its ring slot is
+// still being read by an earlier DMA) is waited for: briefly spinning, then yielding.
+bool CopyPool::drain(bool until_done)
 {
-    const int parts = static_cast<int>(workers_.size()) + 1;
-    if (parts == 1 || bytes < (1u << 20)) {
-        std::memcpy(dst, src, bytes);
-        return;
-    }
-    const size_t chunk = align_up((bytes + parts - 1) / parts, 4096);
-    {
-        std::lock_guard<std::mutex> lk(mu_);
-        for (int i = 0; i < parts - 1; ++i) {
-            const size_t off = std::min(bytes, chunk * (i + 1));
-            const size_t len = std::min(chunk, bytes - off);
-            jobs_[i] = {static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len};
+    const size_t total = pieces_.size();
+    bool copied = false;
+    for (;;) {
+        size_t i = cursor_.load(std::memory_order_relaxed);
+        if (i >= total) return copied;
+        if (!until_done && pieces_[i].chunk >= writable_.load(std::memory_order_acquire)) return copied;
+        if (!cursor_.compare_exchange_weak(i, i + 1, std::memory_order_relaxed)) continue;
+        const Piece& pc = pieces_[i];
+        for (int spins = 0; pc.chunk >= writable_.load(std::memory_order_acquire); ++spins) {
+            if (spins < 256) _mm_pause();
+            else std::this_thread::yield();
         }
-        pending_ = parts - 1;
+        stage_copy(pc.dst, pc.src, pc.bytes);
+        staged_[pc.chunk].fetch_add(1, std::memory_order_release);
+        copied = true;
+        if (!until_done) return copied;
+    }
+}
+
+void CopyPool::begin(std::vector<Piece>&& pieces, const std::vector<uint32_t>& pieces_in_chunk, bool wake)
+{
+    pieces_ = std::move(pieces);
+    pieces_in_chunk_ = pieces_in_chunk;
+    if (staged_capacity_ < pieces_in_chunk_.size()) {
+        staged_capacity_ = std::max<size_t>(64, 2 * pieces_in_chunk_.size());
+        staged_.reset(new std::atomic<uint32_t>[staged_capacity_]);
+    }
+    for (size_t k = 0; k < pieces_in_chunk_.size(); ++k) staged_[k].store(0, std::memory_order_relaxed);
+    cursor_.store(0, std::memory_order_relaxed);
+    writable_.store(0, std::memory_order_relaxed);
+    if (workers_.empty() || !wake) return;
+    {
+        std::lock_guard<std::mutex> lk(mu_);     // publishes the job state above to the workers
+        job_open_ = true;
         ++generation_;
     }
     cv_start_.notify_all();
-    std::memcpy(dst, src, std::min(bytes, chunk));
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
+}
+
+void CopyPool::abort()
+{
+    cursor_.store(pieces_.size(), std::memory_order_relaxed);
+    writable_.store(~size_t(0), std::memory_order_release);
+    end();
+}
+
+// Called once every piece is staged: workers that joined leave at once, late wakers never join.
+void CopyPool::end()
+{
+    if (!workers_.empty()) {
+        std::unique_lock<std::mutex> lk(mu_);     // (no-op for a job the workers were never woken for)
+        job_open_ = false;
+        cv_done_.wait(lk, [&] { return active_ == 0; });
+    }
+    pieces_.clear();
 }
 
 // ---------------------------------------------------------------------------
@@ -266,12 +325,16 @@ Status Engine::init(const pcr_pipeline_desc& d)
     gaussian_variant_ = d.gaussian_kernel;
     comm_mode_ = d.comm_mode;
     gather_root_only_ = d.comm_root_only != 0;
-    slot_points_ = d.ring_slot_points ? static_cast<size_t>(d.ring_slot_points) : (size_t(1) << 19);   // measured best, 8 copy threads
+    // Ring chunk sizes (points), measured on B200 / PCIe Gen5 x16 with 5M-point ingests: staged (pageable)
+    // chunks want to be small so that staging, DMA and kernels overlap early (256 Ki: 2.11 Gpts/s, 2 Mi: 1.85);
+    // direct DMA out of pinned caller memory wants few large copies (256 Ki: 2.16, 2 Mi: 2.37).
+    slot_points_ = d.ring_slot_points ? static_cast<size_t>(d.ring_slot_points) : (size_t(1) << 18);
     slot_points_ = align_up(slot_points_, 1024);
+    direct_points_ = d.ring_slot_points ? slot_points_ : (size_t(1) << 21);
     const int depth = d.ring_depth > 0 ? d.ring_depth : 3;
     ring_.resize(depth);
     staging_threads_ = d.staging_threads > 0 ? d.staging_threads
-                                             : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+                                             : std::max(1u, std::min(12u, std::thread::hardware_concurrency()));
 
     if (exec_mode_ == PCR_EXEC_CPU)
         return Status::error(PCR_NOT_IMPLEMENTED,
@@ -771,81 +834,135 @@ Status Engine::ingest_device(const double* x, const double* y, size_t n,
 Status Engine::ensure_ring()
 {
     if (ring_[0].d) return Status::success();
-    // slot layout: x | y | channel 0 | channel 1 | ...  each segment 256-B aligned
+    // slot layout: x | y | channel 0 | channel 1 | ...  each segment 256-B aligned; the device buffer
+    // also holds the same layout at the direct-DMA chunk size
     const size_t seg64 = align_up(slot_points_ * 8, 256), seg32 = align_up(slot_points_ * 4, 256);
     slot_bytes_ = 2 * seg64 + all_channels_.size() * seg32;
+    const size_t dev_bytes = std::max(slot_bytes_, 2 * align_up(direct_points_ * 8, 256) +
+                                                       all_channels_.size() * align_up(direct_points_ * 4, 256));
     for (Slot& s : ring_) {
         CU_TRY(cudaMallocHost(&s.h, slot_bytes_));
-        CU_TRY(cudaMalloc(&s.d, slot_bytes_));
+        CU_TRY(cudaMalloc(&s.d, dev_bytes));
         CU_TRY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming));
     }
-    if (!pool_) pool_ = new CopyPool(staging_threads_);
+    if (!pool_) pool_ = new CopyPool(staging_threads_ > 1 ? staging_threads_ : 0);   // 1 = the ingesting thread copies
     return Status::success();
 }
 
-// The CUDA-stream ingest ring: chunk k is staged into pinned slot k%depth by the
-// copy pool (skipped when the caller's memory is already pinned), shipped with
-// cudaMemcpyAsync on the copy stream, and consumed by the pass kernels on the
-// compute stream; events order slot reuse.  Replaces PointCloud::to_device_async +
+// The CUDA-stream ingest ring.  Chunk k of the cloud goes through ring slot (pos+k)%depth:
+// staged into the slot's pinned buffer by the copy pool (skipped when the caller's memory
+// is already pinned), shipped with cudaMemcpyAsync on the copy stream, consumed by the pass
+// kernels on the compute stream.  The ingesting thread never blocks on a kernel: re-use of a
+// slot's device buffer is a stream-side wait on its kernel_done event, re-use of its pinned
+// buffer is gated by polling its h2d_done event.  Replaces PointCloud::to_device_async +
 // cudaStreamSynchronize (pipeline.cpp:299-327) and Hybrid mode (pipeline.cpp:785-1152).
 Status Engine::ingest_host(const double* x, const double* y, size_t n,
                            const std::vector<const float*>& cp, bool pinned)
 {
+    if (n == 0) return Status::success();
     ST_TRY(ensure_ring());
-    const size_t seg64 = align_up(slot_points_ * 8, 256), seg32 = align_up(slot_points_ * 4, 256);
+    const size_t chunk = pinned ? direct_points_ : slot_points_;
+    const size_t seg64 = align_up(chunk * 8, 256), seg32 = align_up(chunk * 4, 256);
     const size_t nch = all_channels_.size();
-    size_t k = 0;
-    for (size_t p0 = 0; p0 < n; p0 += slot_points_, ++k) {
-        const size_t cnt = std::min(slot_points_, n - p0);
-        Slot& s = ring_[k % ring_.size()];
-        if (s.used) CU_TRY(cudaEventSynchronize(s.kernel_done));   // slot drained by its last kernels
-        s.used = true;
+    const size_t depth = ring_.size();
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    size_t present = 0;
+    for (size_t c = 0; c < nch; ++c) present += cp[c] ? 1 : 0;
 
+    // H2D + kernels of chunk k; `staged` = the data sits in the slot's pinned buffer
+    auto issue = [&](size_t k, bool staged) -> Status {
+        const size_t p0 = k * chunk, cnt = std::min(chunk, n - p0);
+        Slot& s = ring_[(ring_pos_ + k) % depth];
+        if (s.used) CU_TRY(cudaStreamWaitEvent(copy_, s.kernel_done, 0));   // device buffer drained
         std::vector<const float*> dptr(nch, nullptr);
         double* dxp = reinterpret_cast<double*>(s.d);
         double* dyp = reinterpret_cast<double*>(s.d + seg64);
-        if (pinned) {
-            CU_TRY(cudaMemcpyAsync(dxp, x + p0, cnt * 8, cudaMemcpyHostToDevice, copy_));
-            CU_TRY(cudaMemcpyAsync(dyp, y + p0, cnt * 8, cudaMemcpyHostToDevice, copy_));
+        for (size_t c = 0; c < nch; ++c)
+            if (cp[c]) dptr[c] = reinterpret_cast<float*>(s.d + 2 * seg64 + c * seg32);
+        if (staged && present == nch && cnt == chunk) {
+            // every segment present and full: one contiguous H2D
+            CU_TRY(cudaMemcpyAsync(s.d, s.h, slot_bytes_, cudaMemcpyHostToDevice, copy_));
+        } else {
+            const char* hx = staged ? s.h : reinterpret_cast<const char*>(x + p0);
+            const char* hy = staged ? s.h + seg64 : reinterpret_cast<const char*>(y + p0);
+            CU_TRY(cudaMemcpyAsync(dxp, hx, cnt * 8, cudaMemcpyHostToDevice, copy_));
+            CU_TRY(cudaMemcpyAsync(dyp, hy, cnt * 8, cudaMemcpyHostToDevice, copy_));
             for (size_t c = 0; c < nch; ++c) {
                 if (!cp[c]) continue;
-                float* dc = reinterpret_cast<float*>(s.d + 2 * seg64 + c * seg32);
-                CU_TRY(cudaMemcpyAsync(dc, cp[c] + p0, cnt * 4, cudaMemcpyHostToDevice, copy_));
-                dptr[c] = dc;
-            }
-        } else {
-            // one contiguous H2D when every segment is present; otherwise per segment
-            pool_->copy(s.h, x + p0, cnt * 8);
-            pool_->copy(s.h + seg64, y + p0, cnt * 8);
-            bool all = true;
-            for (size_t c = 0; c < nch; ++c) {
-                if (!cp[c]) { all = false; continue; }
-                pool_->copy(s.h + 2 * seg64 + c * seg32, cp[c] + p0, cnt * 4);
-                dptr[c] = reinterpret_cast<float*>(s.d + 2 * seg64 + c * seg32);
-            }
-            if (all && cnt == slot_points_) {
-                CU_TRY(cudaMemcpyAsync(s.d, s.h, slot_bytes_, cudaMemcpyHostToDevice, copy_));
-            } else {
-                CU_TRY(cudaMemcpyAsync(dxp, s.h, cnt * 8, cudaMemcpyHostToDevice, copy_));
-                CU_TRY(cudaMemcpyAsync(dyp, s.h + seg64, cnt * 8, cudaMemcpyHostToDevice, copy_));
-                for (size_t c = 0; c < nch; ++c)
-                    if (cp[c])
-                        CU_TRY(cudaMemcpyAsync(s.d + 2 * seg64 + c * seg32, s.h + 2 * seg64 + c * seg32,
-                                               cnt * 4, cudaMemcpyHostToDevice, copy_));
+                const char* hc = staged ? s.h + 2 * seg64 + c * seg32 : reinterpret_cast<const char*>(cp[c] + p0);
+                CU_TRY(cudaMemcpyAsync(s.d + 2 * seg64 + c * seg32, hc, cnt * 4, cudaMemcpyHostToDevice, copy_));
             }
         }
-        size_t present = 0;
-        for (size_t c = 0; c < nch; ++c) present += cp[c] ? 1 : 0;
         prof_h2d_ += cnt * (16 + 4 * present);
         CU_TRY(cudaEventRecord(s.h2d_done, copy_));
+        s.h_in_flight = staged;
         CU_TRY(cudaStreamWaitEvent(compute_, s.h2d_done, 0));
         ST_TRY(run_passes(dxp, dyp, cnt, dptr));
         CU_TRY(cudaEventRecord(s.kernel_done, compute_));
+        s.used = true;
+        return Status::success();
+    };
+
+    if (pinned) {
+        for (size_t k = 0; k < nchunks; ++k) ST_TRY(issue(k, false));
+        ring_pos_ = (ring_pos_ + nchunks) % depth;
+        // the caller may reuse its buffers when we return: the DMA out of them must be complete
+        CU_TRY(cudaStreamSynchronize(copy_));
+        return Status::success();
     }
-    // the caller may reuse its buffers when we return: staged copies are already
-    // done; direct DMA from pinned caller memory must have completed.
-    if (pinned) CU_TRY(cudaStreamSynchronize(copy_));
+
+    // pageable: pieces of <= 64 Ki points of one segment of one chunk, in chunk order
+    constexpr size_t kPiecePoints = size_t(1) << 16;
+    std::vector<CopyPool::Piece> pieces;
+    std::vector<uint32_t> per_chunk(nchunks, 0);
+    pieces.reserve(nchunks * (2 + present) * ((chunk + kPiecePoints - 1) / kPiecePoints));
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t p0 = k * chunk, cnt = std::min(chunk, n - p0);
+        Slot& s = ring_[(ring_pos_ + k) % depth];
+        auto cut = [&](char* dst, const char* src, size_t elem) {
+            for (size_t q = 0; q < cnt; q += kPiecePoints) {
+                const size_t m = std::min(kPiecePoints, cnt - q);
+                pieces.push_back({dst + q * elem, src + q * elem, m * elem, static_cast<uint32_t>(k)});
+                ++per_chunk[k];
+            }
+        };
+        cut(s.h, reinterpret_cast<const char*>(x + p0), 8);
+        cut(s.h + seg64, reinterpret_cast<const char*>(y + p0), 8);
+        for (size_t c = 0; c < nch; ++c)
+            if (cp[c]) cut(s.h + 2 * seg64 + c * seg32, reinterpret_cast<const char*>(cp[c] + p0), 4);
+    }
+    // a small cloud is not worth a wake-up: the ingesting thread stages it itself
+    const bool self_serve = pool_->workers() == 0 || n * (16 + 4 * present) < (size_t(1) << 20);
+    pool_->begin(std::move(pieces), per_chunk, !self_serve);
+    struct Closer {       // on an error path: stop handing out pieces, release spinning workers
+        CopyPool* p; bool done = false;
+        ~Closer() { if (!done) p->abort(); }
+    } closer{pool_};
+
+    size_t issued = 0, writable = 0;
+    while (issued < nchunks) {
+        // chunk w may be staged once the DMA that last read its slot's pinned buffer is finished
+        while (writable < nchunks && writable < issued + depth) {
+            Slot& s = ring_[(ring_pos_ + writable) % depth];
+            if (s.h_in_flight) {
+                const cudaError_t q = cudaEventQuery(s.h2d_done);
+                if (q == cudaErrorNotReady) break;
+                CU_TRY(q);
+                s.h_in_flight = false;
+            }
+            pool_->set_writable(++writable);
+        }
+        if (pool_->staged(issued)) {
+            ST_TRY(issue(issued, true));
+            ++issued;
+        } else if (!self_serve || !pool_->help()) {
+            _mm_pause();
+        }
+    }
+    closer.done = true;
+    pool_->end();
+    ring_pos_ = (ring_pos_ + nchunks) % depth;
     return Status::success();
 }
 

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -67,22 +68,48 @@ struct Pass {
     uint32_t* d_combined = nullptr;      // multi-GPU: received peer slices
 };
 
-// Fixed-size worker pool for the pageable -> pinned staging copies.
+// Worker pool for the pageable -> pinned staging copies of one host ingest.
+// The ingest is cut into pieces (one segment range of one ring chunk each); workers
+// pull pieces in order from an atomic cursor and copy them with non-temporal stores.
+// The ingesting thread never copies (unless the pool has no workers): it only gates
+// which chunks may be overwritten (their slot's previous DMA finished) and issues the
+// H2D + kernels of a chunk once all of its pieces are staged.  One wake-up per ingest.
 class CopyPool {
 public:
+    struct Piece { char* dst; const char* src; size_t bytes; uint32_t chunk; };
+
     explicit CopyPool(int threads);
     ~CopyPool();
-    void copy(void* dst, const void* src, size_t bytes);   // parallel memcpy, blocking
-    int threads() const { return static_cast<int>(workers_.size()) + 1; }
+    int workers() const { return static_cast<int>(workers_.size()); }
+
+    // pieces must be ordered by chunk; pieces_in_chunk[k] = number of pieces of chunk k
+    void begin(std::vector<Piece>&& pieces, const std::vector<uint32_t>& pieces_in_chunk, bool wake);
+    void set_writable(size_t chunks) { writable_.store(chunks, std::memory_order_release); }
+    bool staged(size_t chunk) const
+    {
+        return staged_[chunk].load(std::memory_order_acquire) == pieces_in_chunk_[chunk];
+    }
+    bool help() { return drain(false); }   // the caller copies one ready piece; false if none was
+    void end();                             // every piece is staged: release the workers
+    void abort();                           // error path: hand out no more pieces, then end()
+
+    static void stage_copy(void* dst, const void* src, size_t bytes);
+
 private:
-    struct Job { char* dst; const char* src; size_t bytes; };
-    void worker(int idx);
+    void worker();
+    bool drain(bool until_done);
     std::vector<std::thread> workers_;
-    std::vector<Job> jobs_;
+    std::vector<Piece> pieces_;
+    std::vector<uint32_t> pieces_in_chunk_;
+    std::unique_ptr<std::atomic<uint32_t>[]> staged_;
+    size_t staged_capacity_ = 0;
+    std::atomic<size_t> cursor_{0};
+    std::atomic<size_t> writable_{0};
     std::mutex mu_;
     std::condition_variable cv_start_, cv_done_;
     uint64_t generation_ = 0;
-    int pending_ = 0;
+    int active_ = 0;
+    bool job_open_ = false;
     bool stop_ = false;
 };
 
@@ -197,10 +224,13 @@ private:
         char* h = nullptr;   // pinned staging
         char* d = nullptr;   // device chunk
         cudaEvent_t h2d_done = nullptr, kernel_done = nullptr;
-        bool used = false;
+        bool used = false;          // kernel_done has been recorded at least once
+        bool h_in_flight = false;   // h2d_done guards a DMA that is still reading `h`
     };
     std::vector<Slot> ring_;
-    size_t slot_points_ = 0;
+    size_t ring_pos_ = 0;            // next slot; carries over from one ingest to the next
+    size_t slot_points_ = 0;         // staged (pageable) chunk
+    size_t direct_points_ = 0;       // chunk of a direct DMA out of pinned caller memory
     size_t slot_bytes_ = 0;
     CopyPool* pool_ = nullptr;
     int staging_threads_ = 0;
