@@ -332,7 +332,8 @@ Status Engine::init(const pcr_pipeline_desc& d)
     slot_points_ = align_up(slot_points_, 1024);
     direct_points_ = d.ring_slot_points ? slot_points_ : (size_t(1) << 21);
     const int depth = d.ring_depth > 0 ? d.ring_depth : 3;
-    ring_.resize(depth);
+    host_ring_.resize(depth);
+    dev_ring_.resize(std::max(depth, 2));
     staging_threads_ = d.staging_threads > 0 ? d.staging_threads
                                              : std::max(1u, std::min(12u, std::thread::hardware_concurrency()));
 
@@ -503,10 +504,13 @@ Engine::~Engine()
     cudaFree(d_touched_stage_);
     cudaFree(d_out_);
     if (h_out_) cudaFreeHost(h_out_);
-    for (Slot& s : ring_) {
+    for (HostSlot& s : host_ring_) {
         if (s.h) cudaFreeHost(s.h);
-        cudaFree(s.d);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+    }
+    for (DevSlot& s : dev_ring_) {
+        cudaFree(s.d);
+        if (s.filled) cudaEventDestroy(s.filled);
         if (s.kernel_done) cudaEventDestroy(s.kernel_done);
     }
     cudaFree(gs_.keys); cudaFree(gs_.keys_alt); cudaFree(gs_.idx); cudaFree(gs_.idx_alt);
@@ -831,82 +835,114 @@ Status Engine::ingest_device(const double* x, const double* y, size_t n,
     return Status::success();
 }
 
+// Segment layout of a chunk buffer holding `cap` points: x | y | channel 0 | channel 1 | ...,
+// each segment 256-B aligned.
+struct ChunkLayout {
+    size_t seg64, seg32, bytes;
+    ChunkLayout(size_t cap, size_t nch)
+        : seg64(align_up(cap * 8, 256)), seg32(align_up(cap * 4, 256)), bytes(2 * seg64 + nch * seg32) {}
+};
+
 Status Engine::ensure_ring()
 {
-    if (ring_[0].d) return Status::success();
-    // slot layout: x | y | channel 0 | channel 1 | ...  each segment 256-B aligned; the device buffer
-    // also holds the same layout at the direct-DMA chunk size
-    const size_t seg64 = align_up(slot_points_ * 8, 256), seg32 = align_up(slot_points_ * 4, 256);
-    slot_bytes_ = 2 * seg64 + all_channels_.size() * seg32;
-    const size_t dev_bytes = std::max(slot_bytes_, 2 * align_up(direct_points_ * 8, 256) +
-                                                       all_channels_.size() * align_up(direct_points_ * 4, 256));
-    for (Slot& s : ring_) {
+    if (dev_ring_[0].d) return Status::success();
+    // The sort-based passes (Gaussian gather, deterministic Point) are markedly more efficient on larger
+    // batches than a staged chunk (5M-point Gaussian sigma=4, API scope: 645 Mpts/s per 256 Ki chunk, 788 per
+    // 1 Mi), so their kernels run once per group of staged chunks.
+    bool sorted_pass = deterministic_;
+    for (const Pass& p : passes_) sorted_pass = sorted_pass || use_gather(p);
+    group_chunks_ = sorted_pass ? 4 : 1;
+    const size_t nch = all_channels_.size();
+    slot_bytes_ = ChunkLayout(slot_points_, nch).bytes;
+    const size_t dev_bytes = std::max(ChunkLayout(group_chunks_ * slot_points_, nch).bytes,
+                                      ChunkLayout(direct_points_, nch).bytes);
+    for (HostSlot& s : host_ring_) {
         CU_TRY(cudaMallocHost(&s.h, slot_bytes_));
-        CU_TRY(cudaMalloc(&s.d, dev_bytes));
         CU_TRY(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+    }
+    for (DevSlot& s : dev_ring_) {
+        CU_TRY(cudaMalloc(&s.d, dev_bytes));
+        CU_TRY(cudaEventCreateWithFlags(&s.filled, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming));
     }
     if (!pool_) pool_ = new CopyPool(staging_threads_ > 1 ? staging_threads_ : 0);   // 1 = the ingesting thread copies
     return Status::success();
 }
 
-// The CUDA-stream ingest ring.  Chunk k of the cloud goes through ring slot (pos+k)%depth:
-// staged into the slot's pinned buffer by the copy pool (skipped when the caller's memory
-// is already pinned), shipped with cudaMemcpyAsync on the copy stream, consumed by the pass
-// kernels on the compute stream.  The ingesting thread never blocks on a kernel: re-use of a
-// slot's device buffer is a stream-side wait on its kernel_done event, re-use of its pinned
-// buffer is gated by polling its h2d_done event.  Replaces PointCloud::to_device_async +
-// cudaStreamSynchronize (pipeline.cpp:299-327) and Hybrid mode (pipeline.cpp:785-1152).
+// The CUDA-stream ingest ring.  Chunk k of the cloud is staged into pinned buffer (pos+k)%depth by
+// the copy pool (skipped when the caller's memory is already pinned), shipped with cudaMemcpyAsync
+// on the copy stream into the device buffer of its kernel group, and the group is consumed by the
+// pass kernels on the compute stream.  The ingesting thread never blocks on a kernel: re-use of a
+// device buffer is a stream-side wait on its kernel_done event, re-use of a pinned buffer is gated
+// by polling its h2d_done event.  Replaces PointCloud::to_device_async + cudaStreamSynchronize
+// (pipeline.cpp:299-327) and Hybrid mode (pipeline.cpp:785-1152).
 Status Engine::ingest_host(const double* x, const double* y, size_t n,
                            const std::vector<const float*>& cp, bool pinned)
 {
     if (n == 0) return Status::success();
     ST_TRY(ensure_ring());
-    const size_t chunk = pinned ? direct_points_ : slot_points_;
-    const size_t seg64 = align_up(chunk * 8, 256), seg32 = align_up(chunk * 4, 256);
     const size_t nch = all_channels_.size();
-    const size_t depth = ring_.size();
+    const size_t chunk = pinned ? direct_points_ : slot_points_;
+    const size_t group = pinned ? 1 : group_chunks_;              // chunks per kernel group
+    const ChunkLayout hl(slot_points_, nch), dl(group * chunk, nch);
+    const size_t hdepth = host_ring_.size(), ddepth = dev_ring_.size();
     const size_t nchunks = (n + chunk - 1) / chunk;
     size_t present = 0;
     for (size_t c = 0; c < nch; ++c) present += cp[c] ? 1 : 0;
 
-    // H2D + kernels of chunk k; `staged` = the data sits in the slot's pinned buffer
+    // H2D of chunk k and, when it completes its group, the group's kernels.
+    // `staged` = the data sits in the chunk's pinned buffer.
     auto issue = [&](size_t k, bool staged) -> Status {
         const size_t p0 = k * chunk, cnt = std::min(chunk, n - p0);
-        Slot& s = ring_[(ring_pos_ + k) % depth];
-        if (s.used) CU_TRY(cudaStreamWaitEvent(copy_, s.kernel_done, 0));   // device buffer drained
-        std::vector<const float*> dptr(nch, nullptr);
-        double* dxp = reinterpret_cast<double*>(s.d);
-        double* dyp = reinterpret_cast<double*>(s.d + seg64);
-        for (size_t c = 0; c < nch; ++c)
-            if (cp[c]) dptr[c] = reinterpret_cast<float*>(s.d + 2 * seg64 + c * seg32);
-        if (staged && present == nch && cnt == chunk) {
-            // every segment present and full: one contiguous H2D
-            CU_TRY(cudaMemcpyAsync(s.d, s.h, slot_bytes_, cudaMemcpyHostToDevice, copy_));
-        } else {
-            const char* hx = staged ? s.h : reinterpret_cast<const char*>(x + p0);
-            const char* hy = staged ? s.h + seg64 : reinterpret_cast<const char*>(y + p0);
-            CU_TRY(cudaMemcpyAsync(dxp, hx, cnt * 8, cudaMemcpyHostToDevice, copy_));
-            CU_TRY(cudaMemcpyAsync(dyp, hy, cnt * 8, cudaMemcpyHostToDevice, copy_));
-            for (size_t c = 0; c < nch; ++c) {
-                if (!cp[c]) continue;
-                const char* hc = staged ? s.h + 2 * seg64 + c * seg32 : reinterpret_cast<const char*>(cp[c] + p0);
-                CU_TRY(cudaMemcpyAsync(s.d + 2 * seg64 + c * seg32, hc, cnt * 4, cudaMemcpyHostToDevice, copy_));
+        const size_t grp = k / group, sub = k % group;
+        DevSlot& ds = dev_ring_[(dev_pos_ + grp) % ddepth];
+        if (sub == 0 && ds.used) CU_TRY(cudaStreamWaitEvent(copy_, ds.kernel_done, 0));   // buffer drained
+        char* dx = ds.d + sub * chunk * 8;
+        char* dy = ds.d + dl.seg64 + sub * chunk * 8;
+        if (staged) {
+            HostSlot& hs = host_ring_[(host_pos_ + k) % hdepth];
+            if (group == 1 && present == nch && cnt == chunk) {
+                // same layout on both sides, every segment present and full: one contiguous H2D
+                CU_TRY(cudaMemcpyAsync(ds.d, hs.h, slot_bytes_, cudaMemcpyHostToDevice, copy_));
+            } else {
+                CU_TRY(cudaMemcpyAsync(dx, hs.h, cnt * 8, cudaMemcpyHostToDevice, copy_));
+                CU_TRY(cudaMemcpyAsync(dy, hs.h + hl.seg64, cnt * 8, cudaMemcpyHostToDevice, copy_));
+                for (size_t c = 0; c < nch; ++c)
+                    if (cp[c])
+                        CU_TRY(cudaMemcpyAsync(ds.d + 2 * dl.seg64 + c * dl.seg32 + sub * chunk * 4,
+                                               hs.h + 2 * hl.seg64 + c * hl.seg32, cnt * 4,
+                                               cudaMemcpyHostToDevice, copy_));
             }
+            CU_TRY(cudaEventRecord(hs.h2d_done, copy_));
+            hs.in_flight = true;
+        } else {
+            CU_TRY(cudaMemcpyAsync(dx, x + p0, cnt * 8, cudaMemcpyHostToDevice, copy_));
+            CU_TRY(cudaMemcpyAsync(dy, y + p0, cnt * 8, cudaMemcpyHostToDevice, copy_));
+            for (size_t c = 0; c < nch; ++c)
+                if (cp[c])
+                    CU_TRY(cudaMemcpyAsync(ds.d + 2 * dl.seg64 + c * dl.seg32 + sub * chunk * 4, cp[c] + p0,
+                                           cnt * 4, cudaMemcpyHostToDevice, copy_));
         }
         prof_h2d_ += cnt * (16 + 4 * present);
-        CU_TRY(cudaEventRecord(s.h2d_done, copy_));
-        s.h_in_flight = staged;
-        CU_TRY(cudaStreamWaitEvent(compute_, s.h2d_done, 0));
-        ST_TRY(run_passes(dxp, dyp, cnt, dptr));
-        CU_TRY(cudaEventRecord(s.kernel_done, compute_));
-        s.used = true;
+        if (sub + 1 < group && k + 1 < nchunks) return Status::success();     // group still filling
+
+        const size_t g0 = grp * group * chunk, gcnt = std::min(group * chunk, n - g0);
+        std::vector<const float*> dptr(nch, nullptr);
+        for (size_t c = 0; c < nch; ++c)
+            if (cp[c]) dptr[c] = reinterpret_cast<const float*>(ds.d + 2 * dl.seg64 + c * dl.seg32);
+        CU_TRY(cudaEventRecord(ds.filled, copy_));
+        CU_TRY(cudaStreamWaitEvent(compute_, ds.filled, 0));
+        ST_TRY(run_passes(reinterpret_cast<const double*>(ds.d), reinterpret_cast<const double*>(ds.d + dl.seg64),
+                          gcnt, dptr));
+        CU_TRY(cudaEventRecord(ds.kernel_done, compute_));
+        ds.used = true;
         return Status::success();
     };
+    const size_t ngroups = (nchunks + group - 1) / group;
 
     if (pinned) {
         for (size_t k = 0; k < nchunks; ++k) ST_TRY(issue(k, false));
-        ring_pos_ = (ring_pos_ + nchunks) % depth;
+        dev_pos_ = (dev_pos_ + ngroups) % ddepth;
         // the caller may reuse its buffers when we return: the DMA out of them must be complete
         CU_TRY(cudaStreamSynchronize(copy_));
         return Status::success();
@@ -919,7 +955,7 @@ Status Engine::ingest_host(const double* x, const double* y, size_t n,
     pieces.reserve(nchunks * (2 + present) * ((chunk + kPiecePoints - 1) / kPiecePoints));
     for (size_t k = 0; k < nchunks; ++k) {
         const size_t p0 = k * chunk, cnt = std::min(chunk, n - p0);
-        Slot& s = ring_[(ring_pos_ + k) % depth];
+        HostSlot& s = host_ring_[(host_pos_ + k) % hdepth];
         auto cut = [&](char* dst, const char* src, size_t elem) {
             for (size_t q = 0; q < cnt; q += kPiecePoints) {
                 const size_t m = std::min(kPiecePoints, cnt - q);
@@ -928,9 +964,9 @@ Status Engine::ingest_host(const double* x, const double* y, size_t n,
             }
         };
         cut(s.h, reinterpret_cast<const char*>(x + p0), 8);
-        cut(s.h + seg64, reinterpret_cast<const char*>(y + p0), 8);
+        cut(s.h + hl.seg64, reinterpret_cast<const char*>(y + p0), 8);
         for (size_t c = 0; c < nch; ++c)
-            if (cp[c]) cut(s.h + 2 * seg64 + c * seg32, reinterpret_cast<const char*>(cp[c] + p0), 4);
+            if (cp[c]) cut(s.h + 2 * hl.seg64 + c * hl.seg32, reinterpret_cast<const char*>(cp[c] + p0), 4);
     }
     // a small cloud is not worth a wake-up: the ingesting thread stages it itself
     const bool self_serve = pool_->workers() == 0 || n * (16 + 4 * present) < (size_t(1) << 20);
@@ -942,14 +978,14 @@ Status Engine::ingest_host(const double* x, const double* y, size_t n,
 
     size_t issued = 0, writable = 0;
     while (issued < nchunks) {
-        // chunk w may be staged once the DMA that last read its slot's pinned buffer is finished
-        while (writable < nchunks && writable < issued + depth) {
-            Slot& s = ring_[(ring_pos_ + writable) % depth];
-            if (s.h_in_flight) {
+        // chunk w may be staged once the DMA that last read its pinned buffer is finished
+        while (writable < nchunks && writable < issued + hdepth) {
+            HostSlot& s = host_ring_[(host_pos_ + writable) % hdepth];
+            if (s.in_flight) {
                 const cudaError_t q = cudaEventQuery(s.h2d_done);
                 if (q == cudaErrorNotReady) break;
                 CU_TRY(q);
-                s.h_in_flight = false;
+                s.in_flight = false;
             }
             pool_->set_writable(++writable);
         }
@@ -962,7 +998,8 @@ Status Engine::ingest_host(const double* x, const double* y, size_t n,
     }
     closer.done = true;
     pool_->end();
-    ring_pos_ = (ring_pos_ + nchunks) % depth;
+    host_pos_ = (host_pos_ + nchunks) % hdepth;
+    dev_pos_ = (dev_pos_ + ngroups) % ddepth;
     return Status::success();
 }
 

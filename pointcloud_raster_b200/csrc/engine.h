@@ -220,17 +220,24 @@ private:
 
     // ---- streams / ring ----
     cudaStream_t compute_ = nullptr, copy_ = nullptr;
-    struct Slot {
-        char* h = nullptr;   // pinned staging
-        char* d = nullptr;   // device chunk
-        cudaEvent_t h2d_done = nullptr, kernel_done = nullptr;
-        bool used = false;          // kernel_done has been recorded at least once
-        bool h_in_flight = false;   // h2d_done guards a DMA that is still reading `h`
+    // Ingest ring: pinned staging buffers (one staged chunk each) and device buffers (one kernel
+    // group each: several staged chunks, or one direct-DMA chunk out of pinned caller memory).
+    struct HostSlot {
+        char* h = nullptr;
+        cudaEvent_t h2d_done = nullptr;
+        bool in_flight = false;      // h2d_done guards a DMA that may still be reading `h`
     };
-    std::vector<Slot> ring_;
-    size_t ring_pos_ = 0;            // next slot; carries over from one ingest to the next
+    struct DevSlot {
+        char* d = nullptr;
+        cudaEvent_t filled = nullptr, kernel_done = nullptr;
+        bool used = false;           // kernel_done has been recorded at least once
+    };
+    std::vector<HostSlot> host_ring_;
+    std::vector<DevSlot> dev_ring_;
+    size_t host_pos_ = 0, dev_pos_ = 0;   // next slots; carry over from one ingest to the next
     size_t slot_points_ = 0;         // staged (pageable) chunk
     size_t direct_points_ = 0;       // chunk of a direct DMA out of pinned caller memory
+    size_t group_chunks_ = 1;        // staged chunks per kernel group
     size_t slot_bytes_ = 0;
     CopyPool* pool_ = nullptr;
     int staging_threads_ = 0;
