@@ -329,6 +329,10 @@ def run_ours(args):
                      "mean_launch_ms": round(acc_ms, 5),
                      "finalize_mean_ms": round(prof["finalize_ms"] / max(1, int(prof["finalize_launches"])), 5)},
     }
+    if world > 1 and int(prof.get("push_launches", 0)):
+        # N>1: the slice push runs on the ingest stream; the merge/finalize above runs on its own stream under
+        # the next step's ingest kernel
+        out["roofline"]["push_mean_ms"] = round(prof["push_ms"] / int(prof["push_launches"]), 5)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(host_sets[0], budget_s=25.0)
     print(json.dumps(out), flush=True)

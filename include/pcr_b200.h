@@ -154,6 +154,7 @@ typedef struct pcr_profile {
     uint64_t h2d_bytes;         uint64_t d2h_bytes;            /* bytes moved by ingest ring / finalize */
     uint64_t points;                                           /* points fed to accumulate kernels */
     uint64_t kernel_launches;                                  /* every kernel of this library launched */
+    double   push_ms;           uint64_t push_launches;        /* N>1, peer mode: slice push over NVLink */
 } pcr_profile;
 
 typedef struct pcr_pipeline pcr_pipeline;

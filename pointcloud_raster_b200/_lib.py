@@ -73,7 +73,8 @@ class Profile(C.Structure):
                 ("finalize_ms", C.c_double), ("finalize_launches", C.c_uint64),
                 ("init_ms", C.c_double), ("init_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("points", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64),
+                ("push_ms", C.c_double), ("push_launches", C.c_uint64)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.POINTER(Progress), C.c_void_p)

@@ -425,6 +425,14 @@ Status Engine::init(const pcr_pipeline_desc& d)
                              "' is not sm_100-class; this library carries sm_100a code only");
     CU_TRY(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
+    {   // highest priority: once the peers' data is there, the short merge should not queue behind the
+        // CTAs of a concurrently running ingest kernel
+        int lo = 0, hi = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU_TRY(cudaStreamCreateWithPriority(&fin_, cudaStreamNonBlocking, hi));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&e_pushed_, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&e_fin_, cudaEventDisableTiming));
 
     ST_TRY(plan());
     if (deterministic_)
@@ -484,6 +492,15 @@ Status Engine::synchronize()
     ST_TRY(peer_quiesce());
     CU_TRY(cudaStreamSynchronize(copy_));
     CU_TRY(cudaStreamSynchronize(compute_));
+    CU_TRY(cudaStreamSynchronize(fin_));
+    fin_pending_ = false;
+    return Status::success();
+}
+
+Status Engine::join_fin()
+{
+    if (fin_pending_) CU_TRY(cudaStreamWaitEvent(compute_, e_fin_, 0));
+    fin_pending_ = false;
     return Status::success();
 }
 
@@ -493,12 +510,14 @@ Engine::~Engine()
         cudaSetDevice(device_);
         if (copy_) cudaStreamSynchronize(copy_);
         if (compute_) cudaStreamSynchronize(compute_);
+        if (fin_) cudaStreamSynchronize(fin_);
     }
     peer_unmap();
     if (comm_) engine_comm_destroy(nccl_, comm_);
     for (Pass& p : passes_) { cudaFree(p.d_state); cudaFree(p.d_combined); }
     cudaFree(d_touched_);
     cudaFree(d_touched_all_);
+    cudaFree(d_touched_merged_);
     cudaFree(d_flags_);
     cudaFree(d_filter_sets_); cudaFree(d_mask_); cudaFree(d_survivors_);
     cudaFree(d_touched_stage_);
@@ -601,6 +620,7 @@ Status Engine::profile_read(pcr_profile& o)
     o.init_ms = prof_ms_[PROF_INIT];       o.init_launches = prof_n_[PROF_INIT];
     o.h2d_bytes = prof_h2d_; o.d2h_bytes = prof_d2h_; o.points = prof_points_;
     o.kernel_launches = launches_;
+    o.push_ms = prof_ms_[PROF_PUSH];       o.push_launches = prof_n_[PROF_PUSH];
     return Status::success();
 }
 
@@ -617,6 +637,7 @@ Status Engine::timer_end(double& ms)
     CU_TRY(cudaSetDevice(device_));
     if (!timer_a_) return Status::error(PCR_INVALID_ARGUMENT, "pipeline: timer_end without timer_begin");
     CU_TRY(cudaStreamSynchronize(copy_));
+    ST_TRY(join_fin());
     CU_TRY(cudaEventRecord(timer_b_, compute_));
     CU_TRY(cudaEventSynchronize(timer_b_));
     float f = 0.f;
@@ -1011,7 +1032,10 @@ Status Engine::finalize(bool to_host)
     CU_TRY(cudaSetDevice(device_));
     if (world_ > 1) ST_TRY(finalize_multi());
     else ST_TRY(finalize_single());
-    if (to_host || !async_device_ingest_) ST_TRY(peer_quiesce());   // peers' band stores must have landed
+    if (to_host || !async_device_ingest_) {
+        ST_TRY(peer_quiesce());   // peers' band stores must have landed
+        ST_TRY(join_fin());
+    }
     if (to_host) {
         const size_t bytes = reductions_.size() * cells_ * sizeof(float);
         if (!h_out_) CU_TRY(cudaMallocHost(&h_out_, std::max<size_t>(bytes, 4)));

@@ -181,7 +181,7 @@ private:
     int channel_slot(const std::string& name);
 
     // profiling helpers
-    enum ProfKind { PROF_ACC = 0, PROF_SORT = 1, PROF_FIN = 2, PROF_INIT = 3, PROF_KINDS = 4 };
+    enum ProfKind { PROF_ACC = 0, PROF_SORT = 1, PROF_FIN = 2, PROF_INIT = 3, PROF_PUSH = 4, PROF_KINDS = 5 };
     void prof_begin(ProfKind k, cudaStream_t s);
     void prof_end(cudaStream_t s);
     Status prof_collect();
@@ -214,12 +214,19 @@ private:
     std::vector<std::string> all_channels_;   // every channel any pass reads (value + glyph)
     uint32_t* d_touched_ = nullptr;
     uint32_t* d_touched_all_ = nullptr;       // multi-GPU merged flags
+    uint32_t* d_touched_merged_ = nullptr;   // peer mode: OR of every rank's touched-tile flags
     float* d_out_ = nullptr;                  // [bands][cells]
     float* h_out_ = nullptr;                  // pinned, [bands][cells]
     bool finalized_ = false;
 
     // ---- streams / ring ----
     cudaStream_t compute_ = nullptr, copy_ = nullptr;
+    // multi-GPU finalize: the merge/finalize kernels run on their own stream behind the push, so the
+    // next ingest's kernels (compute stream) overlap the wait for the peers
+    cudaStream_t fin_ = nullptr;
+    cudaEvent_t e_pushed_ = nullptr, e_fin_ = nullptr;
+    bool fin_pending_ = false;
+    Status join_fin();                // make the compute stream wait for the last merge/finalize
     // Ingest ring: pinned staging buffers (one staged chunk each) and device buffers (one kernel
     // group each: several staged chunks, or one direct-DMA chunk out of pinned caller memory).
     struct HostSlot {
@@ -265,8 +272,8 @@ private:
     std::vector<ProfSpan> prof_open_;
     std::vector<cudaEvent_t> prof_free_;
     ProfSpan prof_cur_{};
-    double prof_ms_[PROF_KINDS] = {0, 0, 0, 0};
-    uint64_t prof_n_[PROF_KINDS] = {0, 0, 0, 0};
+    double prof_ms_[PROF_KINDS] = {};
+    uint64_t prof_n_[PROF_KINDS] = {};
     uint64_t prof_h2d_ = 0, prof_d2h_ = 0, prof_points_ = 0, launches_ = 0;
     cudaEvent_t timer_a_ = nullptr, timer_b_ = nullptr;
 

@@ -222,6 +222,7 @@ Status Engine::peer_map()
     for (Pass& p : passes_)
         if (!p.d_combined)
             CU_TRY(cudaMalloc(&p.d_combined, static_cast<size_t>(world_) * max_slice * p.layout.width * 4));
+    if (!d_touched_merged_) CU_TRY(cudaMalloc(&d_touched_merged_, std::max(1, n_tiles_) * sizeof(uint32_t)));
     if (!d_touched_stage_) {
         CU_TRY(cudaMalloc(&d_touched_stage_, static_cast<size_t>(world_) * std::max(1, n_tiles_) * 4));
         CU_TRY(cudaMemsetAsync(d_touched_stage_, 0, static_cast<size_t>(world_) * std::max(1, n_tiles_) * 4, compute_));
@@ -289,15 +290,22 @@ void Engine::peer_unmap()
     peer_ok_ = false;
 }
 
-// N>1 finalize over peer memory.  Per call, all on the compute stream, no host sync:
-//   k_push_slices   every record I hold for a row slice owned by rank j is stored straight into
-//                   rank j's combine buffer (posted NVLink writes), my touched-tile flags into
-//                   everyone's staging; the last CTA releases phase 0 on every rank
-//   k_finalize_peer waits until all ranks' pushes have landed here, merges the `world` parts of
-//                   my slice in rank order (Op::merge), finalizes, stores the bands into my array
-//                   and the peers' arrays; the last CTA releases phase 1
-//   (k_peer_wait)   phase 1 from everyone is awaited lazily — by the next push kernel, or by
-//                   peer_quiesce() before the host reads the bands; the next ingest does not wait.
+// N>1 finalize over peer memory.  No host sync anywhere; two streams.
+// Compute stream (behind the ingest kernels):
+//   k_peer_wait     one small kernel: the peers are done reading their combine buffers (phase 1 of
+//                   the previous epoch)
+//   k_push_slices   persistent copy kernel: every record is stored into the combine buffer of the rank
+//                   that owns its row (posted NVLink writes; a local copy for my own slice), my
+//                   touched-tile flags into everyone's staging; the last CTA releases phase 0 on every rank.
+//                   After it the live state is free again: the next ingest's kernels start right here.
+// Finalize stream (highest priority, forked from the compute stream after the push):
+//   k_peer_wait_merge_touched   one small kernel: every rank's push has landed here; OR the touched flags
+//   k_finalize_peer persistent kernel: merges the `world` parts of my slice in rank order (Op::merge),
+//                   finalizes, stores the bands into my array and the peers' arrays; the last CTA
+//                   releases phase 1
+//   (k_peer_wait)   peer_quiesce(): phase 1 from everyone, before the host reads the bands.
+// The compute stream re-joins the finalize stream only where it must: before the next push (my own
+// combine buffer), before a D2H of the bands, in synchronize() and in timer_end().
 Status Engine::finalize_multi_peer()
 {
     ++epoch_;
@@ -316,7 +324,13 @@ Status Engine::finalize_multi_peer()
     slice_rows(grid_.height, world_, rank_, r0, r1);
     const size_t my0 = static_cast<size_t>(r0) * grid_.width, my_cells = static_cast<size_t>(r1 - r0) * grid_.width;
 
-    prof_begin(PROF_FIN, compute_);
+    // ---- compute stream: snapshot every slice into its owner's combine buffer ----
+    ST_TRY(join_fin());     // my previous merge still reads my own combine buffer
+    // The peers' combine buffers may still be read by their previous merge: one small kernel waits for
+    // their "done" flags of the previous epoch (instead of every CTA of the push polling them).
+    ps.waited = 1;
+    prof_begin(PROF_PUSH, compute_);
+    if (epoch_ > 1) { CU_TRY(launch_peer_wait(compute_, ps.pf, 1, epoch_ - 1)); ++launches_; }
     if (passes_.empty()) CU_TRY(launch_peer_signal(compute_, ps.pf, 0, epoch_));
     for (size_t i = 0; i < passes_.size(); ++i) {
         PushTargets pt{};
@@ -324,12 +338,27 @@ Status Engine::finalize_multi_peer()
         pt.rows_per = static_cast<int>(rows_per);
         pt.max_slice_cells = max_slice;
         CU_TRY(launch_push_slices(compute_, passes_[i].d_state, d_touched_, n_tiles_, gp_, passes_[i].layout, pt, ps,
-                                  i == 0, i + 1 == passes_.size()));
+                                  i == 0, i + 1 == passes_.size(), sm_count_));
         ++launches_;
     }
+    prof_end(compute_);
+    CU_TRY(cudaEventRecord(e_pushed_, compute_));
+
+    // ---- finalize stream: wait for the peers' pushes, merge in rank order, finalize, store the bands.
+    //      Nothing below reads the live state (the push snapshotted this rank's own slice as well),
+    //      so the kernels of the next ingest run on the compute stream while this waits on NVLink.
+    CU_TRY(cudaStreamWaitEvent(fin_, e_pushed_, 0));
+    prof_begin(PROF_FIN, fin_);
+    // One small kernel holds the stream until every peer's push has landed (the merge kernel's own CTAs
+    // would all spin on the same flags and occupy the SMs the next ingest wants) and ORs the ranks'
+    // touched-tile flags into one array.
+    CU_TRY(launch_peer_wait_merge_touched(fin_, ps.pf, epoch_, ps.pt, d_touched_merged_, std::max(1, n_tiles_)));
+    ++launches_;
+    ps.pt.n = 1;
+    ps.pt.touched[0] = d_touched_merged_;
     for (size_t i = 0; i < reductions_.size(); ++i)
         if (reductions_[i].rejected)
-            CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), compute_));
+            CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), fin_));
     OutTargets outs{};
     outs.out[outs.n++] = d_out_;
     for (int k = 0; k < world_; ++k) {
@@ -337,23 +366,24 @@ Status Engine::finalize_multi_peer()
         if (gather_root_only_ && k != 0) continue;
         outs.out[outs.n++] = peer_[k].out;
     }
-    if (passes_.empty()) CU_TRY(launch_peer_signal(compute_, ps.pf, 1, epoch_));
+    if (passes_.empty()) CU_TRY(launch_peer_signal(fin_, ps.pf, 1, epoch_));
     for (size_t i = 0; i < passes_.size(); ++i) {
         Pass& p = passes_[i];
         const size_t W = p.layout.width;
         StateParts parts{};
         parts.n = world_;
-        for (int k = 0; k < world_; ++k)
-            parts.part[k] = (k == rank_) ? p.d_state + my0 * W : p.d_combined + static_cast<size_t>(k) * max_slice * W;
+        for (int k = 0; k < world_; ++k) parts.part[k] = p.d_combined + static_cast<size_t>(k) * max_slice * W;
         ps.signal_begin = 0;
         ps.signal_end = i + 1 == passes_.size();
-        CU_TRY(launch_finalize_peer(compute_, parts, my0, my0, my_cells, outs, cells_, gp_, p.layout, p.fin, ps));
+        CU_TRY(launch_finalize_peer(fin_, parts, my0, my0, my_cells, outs, cells_, gp_, p.layout, p.fin, ps, sm_count_));
         ++launches_;
     }
-    prof_end(compute_);
-    // Not awaited here: the peers' "done" flags of this epoch.  My next ingest only touches my own
-    // state, which no peer reads; the flags are awaited by the next push kernel (before it overwrites
-    // the peers' combine buffers) and by peer_quiesce() before the host looks at the bands.
+    prof_end(fin_);
+    CU_TRY(cudaEventRecord(e_fin_, fin_));
+    fin_pending_ = true;
+    // Not awaited here: the peers' "done" flags of this epoch.  They are awaited by the next push kernel
+    // (before it overwrites the peers' combine buffers) and by peer_quiesce() before the host looks at
+    // the bands.
     return Status::success();
 }
 
@@ -363,7 +393,9 @@ Status Engine::peer_quiesce()
     PeerFlags pf{};
     pf.n = world_; pf.rank = rank_;
     for (int k = 0; k < world_; ++k) pf.flags[k] = peer_[k].flags;
-    CU_TRY(launch_peer_wait(compute_, pf, 1, epoch_));
+    CU_TRY(launch_peer_wait(fin_, pf, 1, epoch_));
+    CU_TRY(cudaEventRecord(e_fin_, fin_));
+    fin_pending_ = true;
     ++launches_;
     waited_epoch_ = epoch_;
     return Status::success();

@@ -98,11 +98,13 @@ struct PeerSync {
     int signal_end;                  // the last CTA of this launch announces "I am done with your
                                      // state and your bands hold my slice" (last pass)
     unsigned int* done_counter;      // CTAs finished so far (self-resetting)
+    int waited;                      // a k_peer_wait* launch ahead of this one on the stream already
+                                     // observed the flags: the CTAs do not poll them again
 };
 cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t part_cell0, size_t cell0,
                                  size_t count, const OutTargets& out, size_t band_stride,
                                  const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
-                                 const PeerSync& ps);
+                                 const PeerSync& ps, int sm_count);
 
 // Push phase of the peer-memory combine: every record of `state` that belongs to another rank's
 // row slice is stored (posted NVLink writes, no round trip) into that rank's combine buffer, slot
@@ -116,7 +118,7 @@ struct PushTargets {
 };
 cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint32_t* touched, int n_tiles,
                                const GridParams& g, const PassLayout& L, const PushTargets& pt,
-                               const PeerSync& ps, bool push_touched, bool signal);
+                               const PeerSync& ps, bool push_touched, bool signal, int sm_count);
 
 // store `epoch` into slot (phase, my rank) of every rank's flag array (system-scope release)
 cudaError_t launch_peer_signal(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch);

@@ -174,7 +174,8 @@ __device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch)
 // order, finalizes, and stores the bands into this rank's and the peers' arrays (posted NVLink
 // writes); the last CTA to finish releases the "done" flag on every rank.
 
-// Push: thread per cell of the WHOLE grid; cells owned by another rank are copied to that rank.
+// Push: thread per cell of the WHOLE grid; every cell's record is copied to the rank that owns its row
+// (NVLink stores for foreign slices, a local copy for this rank's own slice).
 template <int W>
 __global__ void __launch_bounds__(kThreads)
 k_push_slices(const uint32_t* __restrict__ state, const uint32_t* __restrict__ touched, int n_tiles,
@@ -185,26 +186,29 @@ k_push_slices(const uint32_t* __restrict__ state, const uint32_t* __restrict__ t
     // The peers' combine buffers may still be being read by their previous finalize: wait for
     // their "done" flags of the previous epoch (phase 1) before overwriting them.  Nothing else
     // of the previous finalize is waited for here, so the ingest in between ran unhindered.
-    if (ps.epoch > 1) {
+    if (ps.epoch > 1 && !ps.waited) {
         if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + kMaxParts + threadIdx.x, ps.epoch - 1);
         __syncthreads();
     }
-    const size_t cells = static_cast<size_t>(g.width) * g.height;
-    const size_t cell = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
-    if (cell < cells) {
-        const int row = static_cast<int>(cell / static_cast<size_t>(g.width));
-        const int owner = row / pt.rows_per;
-        if (owner != pf.rank) {
-            const size_t local = cell - static_cast<size_t>(owner) * pt.rows_per * g.width;
-            uint32_t* dst = pt.combined[owner] + (static_cast<size_t>(pf.rank) * pt.max_slice_cells + local) * W;
-            const uint32_t* src = state + cell * W;
-            if constexpr (W == 1) dst[0] = src[0];
-            if constexpr (W == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
-            if constexpr (W == 4) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-            if constexpr (W == 8) {
-                reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
-                reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
-            }
+    // Persistent grid-stride loop (cells < 2^32, engine check): one system fence per CTA at the end
+    // instead of one per 256 cells, and no CTA turnover while the posted NVLink stores drain.
+    const unsigned cells = static_cast<unsigned>(g.width) * static_cast<unsigned>(g.height);
+    const unsigned per_owner = static_cast<unsigned>(pt.rows_per) * static_cast<unsigned>(g.width);
+    const unsigned stride = gridDim.x * kThreads;
+    for (unsigned cell = blockIdx.x * kThreads + threadIdx.x; cell < cells; cell += stride) {
+        // every cell's record goes to the rank that owns its row: NVLink stores for foreign slices, a
+        // local copy for my own (after this kernel nothing of this finalize reads the live state, so
+        // the next ingest may overlap the merge)
+        const unsigned owner = cell / per_owner;
+        const unsigned local = cell - owner * per_owner;
+        uint32_t* dst = pt.combined[owner] + (static_cast<size_t>(pf.rank) * pt.max_slice_cells + local) * W;
+        const uint32_t* src = state + static_cast<size_t>(cell) * W;
+        if constexpr (W == 1) dst[0] = src[0];
+        if constexpr (W == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+        if constexpr (W == 4) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        if constexpr (W == 8) {
+            reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
+            reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
         }
     }
     if (push_touched && blockIdx.x == 0) {
@@ -238,11 +242,14 @@ k_finalize_peer(const __grid_constant__ StateParts parts, size_t part_cell0, siz
 {
     __shared__ uint32_t s_words[W][kThreads];
     const PeerFlags& pf = ps.pf;
-    if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + threadIdx.x, ps.epoch);
-    __syncthreads();
+    if (!ps.waited) {
+        if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + threadIdx.x, ps.epoch);
+        __syncthreads();
+    }
 
-    const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
-    if (i < count) {
+    // persistent grid-stride loop: one system fence per CTA behind all of its remote band stores
+    const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < count; i += stride) {
         const size_t cell = cell0 + i;
         const unsigned row = static_cast<unsigned>(cell) / static_cast<unsigned>(g.width);
         const unsigned col = static_cast<unsigned>(cell) - row * static_cast<unsigned>(g.width);
@@ -351,11 +358,12 @@ cudaError_t launch_filter_mask(cudaStream_t s, const FilterProgram& fp, size_t n
 }
 
 cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint32_t* touched, int n_tiles,
-                               const GridParams& g, const PassLayout& L, const PushTargets& pt,
-                               const PeerSync& ps, bool push_touched, bool signal)
+                               const GridParams& g, const PassLayout& L, const PushTargets& pt, const PeerSync& ps,
+                               bool push_touched, bool signal, int sm_count)
 {
     const size_t cells = static_cast<size_t>(g.width) * g.height;
-    const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, (cells + kThreads - 1) / kThreads));
+    const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((cells + kThreads - 1) / kThreads,
+                                                                                     static_cast<size_t>(sm_count) * 8)));
     switch (L.width) {
     case 1: k_push_slices<1><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
     case 2: k_push_slices<2><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
@@ -369,10 +377,11 @@ cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint
 cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t part_cell0, size_t cell0,
                                  size_t count, const OutTargets& out, size_t band_stride,
                                  const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
-                                 const PeerSync& ps)
+                                 const PeerSync& ps, int sm_count)
 {
     // count may be 0 (a rank that owns no rows): the handshake still has to happen
-    const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, (count + kThreads - 1) / kThreads));
+    const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((count + kThreads - 1) / kThreads,
+                                                                                     static_cast<size_t>(sm_count) * 8)));
     switch (L.width) {
     case 1: k_finalize_peer<1><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
     case 2: k_finalize_peer<2><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;

@@ -120,7 +120,7 @@ def test_slice_rows_cover_grid(pcr):
 
 
 # ---- the real N>1 path on GPUs ------------------------------------------------------------------
-def _gpu_worker(rank, world, id_path, out_dir, deterministic, comm_mode):
+def _gpu_worker(rank, world, id_path, out_dir, deterministic, comm_mode, overlapped=False):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
     import time
     from pointcloud_raster_b200 import pcr
@@ -143,23 +143,41 @@ def _gpu_worker(rank, world, id_path, out_dir, deterministic, comm_mode):
         specs.append(pcr.gaussian_splat_spec("value", default_sigma=1.5, max_radius_cells=5.0))
     cfg = pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = specs; cfg.exec_mode = pcr.ExecutionMode.GPU
     cfg.cuda_device_id = rank; cfg.deterministic = deterministic; cfg.comm_mode = comm_mode
+    cfg.async_ingest = overlapped
     p = pcr.Pipeline.create(cfg)
     assert p is not None
     p.comm_init(uid, rank, world)
     lo, hi = rank * n // world, (rank + 1) * n // world
-    half = (lo + hi) // 2                      # two ingest+finalize rounds: the combine must be repeatable
-    p.ingest(mk(pcr, x[lo:half], y[lo:half], {k: v[lo:half] for k, v in ch.items()}))
-    p.finalize()
-    p.ingest(mk(pcr, x[half:hi], y[half:hi], {k: v[half:hi] for k, v in ch.items()}))
-    p.finalize()
+    if overlapped:
+        # bench.py's loop: device-resident clouds, ingest + finalize_device back to back without any host
+        # sync, so the merge of round r (finalize stream) runs under the ingest kernels of round r+1
+        edges = np.linspace(lo, hi, 9).astype(int)
+        parts = [mk(pcr, x[a:b], y[a:b], {k: v[a:b] for k, v in ch.items()}).to_device(rank)
+                 for a, b in zip(edges, edges[1:])]
+        for c in parts:
+            p.ingest(c)
+            p.finalize_device()
+        p.synchronize()
+        p.finalize()
+    else:
+        half = (lo + hi) // 2                      # two ingest+finalize rounds: the combine must be repeatable
+        p.ingest(mk(pcr, x[lo:half], y[lo:half], {k: v[lo:half] for k, v in ch.items()}))
+        p.finalize()
+        p.ingest(mk(pcr, x[half:hi], y[half:hi], {k: v[half:hi] for k, v in ch.items()}))
+        p.finalize()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), *[np.array(p.result().band_array(i)) for i in range(len(specs))])
     p.comm_barrier()
 
 
 @pytest.mark.gpu
+def test_multi_gpu_overlapped_steps_match_oracle(gpu_pcr, oracle):
+    test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, False, 2, overlapped=True)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("comm_mode", [1, 2], ids=["nccl", "peer"])
 @pytest.mark.parametrize("deterministic", [False, True])
-def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_mode):
+def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_mode, overlapped=False):
     if gpu_pcr.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     import multiprocessing as mp
@@ -168,7 +186,7 @@ def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_
     world = min(gpu_pcr.device_count(), 4)
     ctx = mp.get_context("spawn")
     with tempfile.TemporaryDirectory() as d:
-        procs = [ctx.Process(target=_gpu_worker, args=(r, world, os.path.join(d, "id"), d, deterministic, comm_mode))
+        procs = [ctx.Process(target=_gpu_worker, args=(r, world, os.path.join(d, "id"), d, deterministic, comm_mode, overlapped))
                  for r in range(world)]
         for pr in procs: pr.start()
         for pr in procs: pr.join(300)
