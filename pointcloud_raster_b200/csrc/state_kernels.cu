@@ -129,6 +129,66 @@ k_finalize(const __grid_constant__ StateParts parts, size_t part_cell0, size_t c
     finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live, s_words);
 }
 
+// Single-GPU finalize, four consecutive cells per thread: one 128-bit store per band instead of
+// four 32-bit ones (the kernel is store-issue bound: W record words in, one word per band out).
+// Requires cell0, count and band_stride to be multiples of 4.
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+k_finalize_v4(const uint32_t* __restrict__ part, size_t part_cell0, size_t cell0, size_t groups,
+              float* __restrict__ out, size_t band_stride, const __grid_constant__ GridParams g,
+              const __grid_constant__ PassLayout L, const __grid_constant__ FinalizeProgram fp,
+              const uint32_t* __restrict__ touched)
+{
+    __shared__ uint32_t s_words[W * 4][kThreads];          // [word][cell of the group][thread]
+    const size_t gi = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+    if (gi >= groups) return;
+    const size_t cell = cell0 + 4 * gi;
+    bool live[4];
+    if (g.tiles_x * g.tiles_y == 1) {
+        live[0] = live[1] = live[2] = live[3] = touched[0] != 0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned at = static_cast<unsigned>(cell) + c;
+            const unsigned row = at / static_cast<unsigned>(g.width);
+            const unsigned col = at - row * static_cast<unsigned>(g.width);
+            live[c] = touched[tile_of(g, static_cast<int>(col), static_cast<int>(row))] != 0;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t r[8];
+        load_record<W>(part, cell + c - part_cell0, r);
+#pragma unroll
+        for (int j = 0; j < W; ++j) s_words[j * 4 + c][threadIdx.x] = r[j];   // own column only: no sync needed
+    }
+    const float nan = __int_as_float(0x7fc00000);
+    for (int b = 0; b < fp.n; ++b) {
+        const int kind = fp.kind[b];
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            o[c] = nan;
+            if (!live[c]) continue;
+            const uint32_t wa = s_words[fp.word_a[b] * 4 + c][threadIdx.x];
+            const float a = __uint_as_float(wa);
+            if (kind == FIN_SUM) {
+                o[c] = a;
+            } else if (kind == FIN_COUNT) {
+                o[c] = a > 0.0f ? a : nan;
+            } else if (kind == FIN_RATIO) {
+                const float d = __uint_as_float(s_words[fp.word_b[b] * 4 + c][threadIdx.x]);
+                o[c] = d > 0.0f ? __fdiv_rn(a, d) : nan;
+            } else {
+                const float m = ordered_f32(static_cast<int32_t>(wa));
+                o[c] = (m == (kind == FIN_MAX ? -FLT_MAX : FLT_MAX)) ? nan : m;
+            }
+        }
+        *reinterpret_cast<float4*>(out + static_cast<size_t>(fp.band[b]) * band_stride + cell) =
+            make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // Point filter -> byte mask (evaluate_predicate, src/engine/filter.cpp:37-58; predicates are AND-ed)
 __global__ void __launch_bounds__(kThreads)
 k_filter_mask(const __grid_constant__ FilterProgram fp, size_t n, uint8_t* __restrict__ mask,
@@ -333,6 +393,18 @@ cudaError_t launch_finalize(cudaStream_t s, const StateParts& parts, size_t part
                             const uint32_t* touched)
 {
     if (count == 0) return cudaSuccess;
+    if (parts.n == 1 && out.n == 1 && cell0 % 4 == 0 && count % 4 == 0 && band_stride % 4 == 0 &&
+        (cell0 - part_cell0) % 4 == 0 && L.width <= 4) {
+        const size_t groups = count / 4;
+        const unsigned vgrid = static_cast<unsigned>((groups + kThreads - 1) / kThreads);
+        switch (L.width) {
+        case 1: k_finalize_v4<1><<<vgrid, kThreads, 0, s>>>(parts.part[0], part_cell0, cell0, groups, out.out[0], band_stride, g, L, fp, touched); break;
+        case 2: k_finalize_v4<2><<<vgrid, kThreads, 0, s>>>(parts.part[0], part_cell0, cell0, groups, out.out[0], band_stride, g, L, fp, touched); break;
+        case 4: k_finalize_v4<4><<<vgrid, kThreads, 0, s>>>(parts.part[0], part_cell0, cell0, groups, out.out[0], band_stride, g, L, fp, touched); break;
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     const unsigned grid = static_cast<unsigned>((count + kThreads - 1) / kThreads);
     switch (L.width) {
     case 1: k_finalize<1><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, touched); break;
