@@ -974,6 +974,13 @@ def device_count() -> int:
     return int(lib.pcr_device_count())
 
 
+def device_mem_info(device=0):
+    """(free_bytes, total_bytes) of a GPU — cuda_get_memory_info, include/pcr/core/types.h:186-201."""
+    free, total = C.c_uint64(0), C.c_uint64(0)
+    check(lib.pcr_device_mem_info(int(device), C.byref(free), C.byref(total)))
+    return free.value, total.value
+
+
 def device_name(device=0) -> str:
     buf = C.create_string_buffer(256)
     lib.pcr_device_name(int(device), buf, 256)

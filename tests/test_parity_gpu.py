@@ -381,3 +381,97 @@ def test_full_size_point_config(gpu_pcr, oracle):
     from util import cloud as mk
     p.ingest(mk(gpu_pcr, x, y, ch)); p.finalize()
     assert np.array_equal(np.array(p.result().band_array(1)), 2 * ref[1], equal_nan=True)
+
+
+# ---- BASELINE config 3 at full size: 5M lines, half length 16, per-point direction ------------------
+def test_full_size_line_config(gpu_pcr, oracle):
+    gc = make_grid(gpu_pcr, 1000, 1000)
+    x, y, ch = uniform_cloud(5_000_000, 1000, 1000, seed=42)
+    ch["hl"] = np.full(len(x), 16.0, np.float32)
+    specs = []
+    for t in ("WeightedAverage", "Count"):
+        s = gpu_pcr.line_splat_spec("value", "direction", "hl", max_radius_cells=18.0)
+        s.type = getattr(gpu_pcr.ReductionType, t)
+        specs.append(s)
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, [(x, y, ch)], specs)               # 165M cell visits: a few seconds in the C oracle
+    got, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs)
+    painted = float(np.nansum(ref[1].astype(np.float64)))
+    flips = float(np.nansum(np.abs(np.nan_to_num(got[1]).astype(np.float64) - np.nan_to_num(ref[1]))))
+    assert painted > 1.4e8                                  # ~29.6 cells per line
+    assert flips <= max(2.0, 1e-6 * painted), (flips, painted)
+    if flips == 0:                                          # same cell sets: the averages must agree cell by cell
+        compare_bands(oracle, gd, [(x, y, ch)], specs, ref, got, "config 3 full size", device_weights=True)
+
+
+# ---- BASELINE config 4 at full size: 5M Gaussians, sigma 4 and 16, radius cap 32 ---------------------
+# The oracle needs minutes for 21G cell visits, so at full size the two independent device
+# implementations (scatter: per-point REDs; gather: tile-binned tensor-core products) check each other,
+# cell by cell against the weight mass, next to exact invariants; both are checked against the oracle at
+# smaller sizes above.
+@pytest.mark.parametrize("sigma", [4.0, 16.0])
+def test_full_size_gaussian_config(gpu_pcr, sigma):
+    from util import GLYPH_WEIGHT_RTOL
+    gc = make_grid(gpu_pcr, 1000, 1000)
+    x, y, ch = uniform_cloud(5_000_000, 1000, 1000, seed=42)
+    ch["sigma"] = np.full(len(x), sigma, np.float32)
+    specs = []
+    for t in ("Sum", "Count", "WeightedAverage"):
+        s = gpu_pcr.gaussian_splat_spec("value", "sigma", "sigma", max_radius_cells=32.0)
+        s.type = getattr(gpu_pcr.ReductionType, t)
+        specs.append(s)
+    scatter, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs, gaussian_kernel=1)
+    gather, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs, gaussian_kernel=2)
+    mass = gather[1].astype(np.float64)                     # sum of weights per cell; values are in [0,1]
+    assert not np.isnan(mass).any() and mass.min() > 0
+    n_terms = (2 * min(3 * sigma, 32.0) + 1) ** 2 * 5.0     # ~ footprint cells x points per cell
+    tol = (GLYPH_WEIGHT_RTOL + 2 * n_terms * 2.0 ** -24) * mass
+    for k in (0, 1):
+        assert (np.abs(scatter[k].astype(np.float64) - gather[k]) <= tol).all(), (sigma, k)
+    # WeightedAverage = Sum / Count of the same run, bit for bit (same state words, one IEEE division)
+    assert np.array_equal(gather[2], (gather[0] / gather[1]).astype(np.float32))
+    assert np.abs(scatter[2].astype(np.float64) - gather[2]).max() <= 1e-4
+    # a weighted average of values in [0,1) stays in [0,1); total weight mass is the sum of the kernels
+    assert gather[2].min() >= 0.0 and gather[2].max() < 1.0
+    # interior points carry the full kernel; its mass is the product of two 1-D sums (no clipping away
+    # from the border), identical for every point up to the sub-cell offset: compare totals
+    total = mass.sum()
+    assert abs(total - scatter[1].astype(np.float64).sum()) <= 1e-6 * total
+    # gather is deterministic: a second run reproduces every bit
+    again, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs, gaussian_kernel=2)
+    for a, b in zip(gather, again):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+# ---- BASELINE config 5 at single-GPU scale: 20000 x 20000 grid (25 reference tiles), clustered ----
+def test_config5_like_large_grid(gpu_pcr):
+    W = 20000
+    free, _total = gpu_pcr.device_mem_info()
+    if free < 16 << 30:
+        pytest.skip("needs 16 GB of free HBM")
+    gc = make_grid(gpu_pcr, W, W)
+    assert (gc.tiles_x, gc.tiles_y) == (5, 5)
+    n = 20_000_000
+    x, y, ch = clustered_cloud(n, W, W, seed=5, k=12)
+    R = gpu_pcr.ReductionType
+    specs = [spec(gpu_pcr, "value", R.Average), spec(gpu_pcr, "value", R.Max), spec(gpu_pcr, "value", R.Count)]
+    got, p = run_product(gpu_pcr, gc, [(x, y, ch)], specs)
+    ok = (x >= 0) & (x <= W) & (y >= 0) & (y <= W)
+    col = np.minimum(np.floor(x[ok]).astype(np.int64), W - 1)
+    row = np.minimum(np.floor(W - y[ok]).astype(np.int64), W - 1)      # (y - max_y) / -1
+    cells, inverse, counts = np.unique(row * W + col, return_inverse=True, return_counts=True)
+    cnt = got[2].reshape(-1)
+    assert np.count_nonzero(~np.isnan(cnt)) == len(cells)                 # Count finalizes empty cells to NaN
+    assert np.array_equal(cnt[cells], counts.astype(np.float32))          # exact, every cell
+    mx = np.full(len(cells), -np.inf, np.float32)
+    np.maximum.at(mx, inverse, ch["value"][ok])
+    assert np.array_equal(got[1].reshape(-1)[cells], mx)                  # Max bit-exact
+    sums = np.bincount(inverse, weights=ch["value"][ok].astype(np.float64))
+    avg = got[0].reshape(-1)[cells].astype(np.float64)
+    assert (np.abs(avg - sums / counts) <= 2 * counts * 2.0 ** -24 * 1.5 + 1e-6).all()   # any-order fp32 sum bound
+    # touched-tile rule (R11): Max/Average are NaN wherever Count is; untouched 4096-cell tiles are all NaN
+    assert np.array_equal(np.isnan(got[0]), np.isnan(got[2])) and np.array_equal(np.isnan(got[1]), np.isnan(got[2]))
+    assert p.stats().points_processed == n
+    touched = np.zeros((5, 5), bool)
+    touched[np.minimum(row // 4096, 4), np.minimum(col // 4096, 4)] = True
+    assert p.stats().tiles_active == int(touched.sum())
