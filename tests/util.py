@@ -173,6 +173,15 @@ def compare_bands(oracle, gd, clouds, specs, ref_bands, got_bands, what, device_
         else:
             _, a64, cnt = oracle.bounds(gd, clouds, s, want_weight=(t == orc.COUNT))
             tol = sum_tolerance(a64, cnt) + extra * a64 + np.abs(ref.astype(np.float64)) * 2.0 ** -23
+        if t not in (orc.AVERAGE, orc.WEIGHTED_AVERAGE):
+            # Rounding is unbiased, a different accumulation rule is not: the mean SIGNED error over many
+            # cells, relative to the summed magnitudes, must vanish (this is what caught the tensor core's
+            # truncating accumulate in the Gaussian gather: -6e-5 there).
+            m = np.isfinite(ref) & np.isfinite(got) & (a64 > 0)
+            if int(m.sum()) >= 1000:
+                with np.errstate(all="ignore"):
+                    bias = float(np.mean((got[m].astype(np.float64) - ref[m].astype(np.float64)) / a64[m]))
+                assert abs(bias) <= 2.0 ** -21, f"{tag}: systematic bias {bias:.3e} relative to sum|x|"
         bad = np.isnan(ref) != np.isnan(got)
         fin = np.isfinite(ref) & np.isfinite(got)
         with np.errstate(all="ignore"):
