@@ -9,12 +9,15 @@ File formats follow src/io/point_cloud_io.cpp of the reference:
 PointCloudReader streams PCRP in chunks by SEEKING into each SoA array; the reference's
 read_chunk_pcr (:574-612) reads x, y and the channels back to back from the current position, which
 is only right when one chunk covers the whole file — that defect is not reproduced.  LAS/LAZ are
-NotImplemented upstream as well.  Host-side numpy code: file IO sits in front of the hot path.
+NotImplemented upstream; uncompressed LAS is read (and written, format 0) here through _las.py, LAZ
+stays NotImplemented.  Host-side numpy code: file IO sits in front of the hot path.
 """
 import os
 import struct
 
 import numpy as np
+
+from . import _las
 
 MAGIC = 0x50524350
 
@@ -90,6 +93,23 @@ def read_point_cloud_info(path, fmt=4):
             raise RuntimeError("CSV must start with x,y columns")
         info.num_points = n
         info.channels = [ChannelDesc(nm, DataType.Float64) for nm in header[2:]]
+    elif fmt == PointCloudFormat.LAS:
+        try:
+            with open(path, "rb") as f:
+                h = _las.read_header(f)
+        except OSError:
+            raise RuntimeError(f"failed to open file: {path}")
+        if h.compressed:
+            raise RuntimeError("LAZ (compressed LAS) format not yet implemented")
+        info.num_points = int(h.num_points)
+        names = list(_las.CHANNELS) + (["gps_time"] if "gps_time" in _las.record_dtype(h).names else [])
+        info.channels = [ChannelDesc(nm, DataType.Float32) for nm in names]
+        if h.epsg:
+            info.crs = CRS.from_epsg(h.epsg)
+        info.bounds = BBox()
+        if info.num_points:
+            info.bounds.min_x, info.bounds.min_y, info.bounds.max_x, info.bounds.max_y = h.min_x, h.min_y, h.max_x, h.max_y
+        return info
     else:
         raise RuntimeError("LAS/LAZ format not yet implemented")
     info.bounds = BBox()          # not stored in either format
@@ -131,6 +151,12 @@ def write_point_cloud(path, cloud, fmt=0):
             f.write(",".join(["x", "y"] + names) + "\n")
             for row in zip(*cols):
                 f.write(",".join(f"{v:.15g}" for v in row) + "\n")
+    elif fmt == PointCloudFormat.LAS:
+        ch = {}
+        for nm in names:
+            desc, storage = cloud._channels[nm]
+            ch[nm] = np.asarray(cloud._view(storage, NP[desc.dtype], n), np.float64)
+        _las.write(path, cloud.x_array(), cloud.y_array(), ch, epsg=cloud.crs().epsg)
     else:
         raise RuntimeError("LAS/LAZ format not yet implemented")
 
@@ -171,6 +197,10 @@ class PointCloudReader:
             if r._fmt == PointCloudFormat.PCR_Binary:
                 r._f = open(path, "rb")
                 _, _, _, r._body = _read_pcrp_header(r._f)
+            elif r._fmt == PointCloudFormat.LAS:
+                r._f = open(path, "rb")
+                r._las = _las.read_header(r._f)
+                r._body = r._las.point_offset
             else:
                 r._f = open(path)
                 r._f.readline()
@@ -213,6 +243,19 @@ class PointCloudReader:
                 desc, storage = cloud._channels[ch.name]
                 cloud._store(storage, NP[desc.dtype], grab(off, dt), ch.name)
                 off += n_total * dt.itemsize
+        elif self._fmt == PointCloudFormat.LAS:
+            dt = _las.record_dtype(self._las)
+            self._f.seek(self._body + self._pos * dt.itemsize)
+            recs = np.frombuffer(self._f.read(cnt * dt.itemsize), dtype=dt)
+            cnt = len(recs)
+            x, y, ch = _las.decode(self._las, recs)
+            if "gps_time" in dt.names:
+                ch["gps_time"] = recs["gps_time"].astype(np.float32)
+            cloud.set_x_array(x)
+            cloud.set_y_array(y)
+            for nm, arr in ch.items():
+                desc, storage = cloud._channels[nm]
+                cloud._store(storage, NP[desc.dtype], arr, nm)
         else:
             rows = []
             while len(rows) < cnt:

@@ -72,7 +72,10 @@ def test_io_errors(pcr, tmp_path):
     with pytest.raises(RuntimeError, match="Failed to open"):
         pcr.PointCloudReader.open(str(tmp_path / "missing.pcr"))
     with pytest.raises(RuntimeError, match="LAS"):
-        pcr.read_point_cloud_info(str(tmp_path / "x.las"))
+        pcr.read_point_cloud_info(str(tmp_path / "x.laz"))            # compressed LAS: as upstream, not implemented
+    notlas = tmp_path / "x.las"; notlas.write_bytes(b"\0" * 300)
+    with pytest.raises(RuntimeError, match="LASF"):
+        pcr.read_point_cloud_info(str(notlas))
     csv = tmp_path / "c.csv"; csv.write_text("a,b\n1,2\n")
     with pytest.raises(RuntimeError, match="x,y columns"):
         pcr.read_point_cloud_info(str(csv))
@@ -114,3 +117,81 @@ def test_stream_file_into_pipeline(gpu_pcr, tmp_path):
     for b in range(2):
         assert np.array_equal(np.array(whole.result().band_array(b)), np.array(streamed.result().band_array(b)), equal_nan=True)
     assert streamed.stats().points_processed == n
+
+
+# ---- LAS (uncompressed): NotImplemented upstream, read here --------------------------------------
+def test_las_roundtrip_and_streaming(pcr, tmp_path):
+    rng = np.random.default_rng(3)
+    n = 5000
+    x = np.round(rng.uniform(500000, 500100, n), 3)          # mm grid: the LAS quantisation is then exact
+    y = np.round(rng.uniform(4100000, 4100080, n), 3)
+    c = pcr.PointCloud.create(n)
+    c.set_x_array(x); c.set_y_array(y)
+    vals = {"z": np.round(rng.uniform(10, 90, n), 3), "intensity": rng.integers(0, 65535, n),
+            "classification": rng.integers(0, 19, n), "return_number": rng.integers(1, 6, n),
+            "number_of_returns": rng.integers(1, 6, n)}
+    for k, v in vals.items():
+        c.add_channel(k, pcr.DataType.Float32); c.set_channel_array_f32(k, v.astype(np.float32))
+    c.set_crs(pcr.CRS.from_epsg(32610))
+    path = str(tmp_path / "cloud.las")
+    pcr.write_point_cloud(path, c, pcr.PointCloudFormat.LAS)
+    info = pcr.read_point_cloud_info(path)
+    assert info.num_points == n and info.crs.epsg == 32610
+    assert [ch.name for ch in info.channels] == ["z", "intensity", "classification", "return_number", "number_of_returns"]
+    assert abs(info.bounds.min_x - x.min()) < 1e-6 and abs(info.bounds.max_y - y.max()) < 1e-6
+    back = pcr.read_point_cloud(path)                        # format auto-detected from the extension
+    assert back.count() == n
+    assert np.abs(back.x_array() - x).max() < 1e-6 and np.abs(back.y_array() - y).max() < 1e-6
+    for k, v in vals.items():
+        assert np.allclose(back.channel_array_f32(k), v.astype(np.float32), atol=2e-3 if k == "z" else 0), k
+    r = pcr.PointCloudReader.open(path)
+    chunk = pcr.PointCloud.create(1024)
+    got, xs = 0, []
+    while not r.eof():
+        m = r.read_chunk(chunk, 1024)
+        xs.append(np.array(chunk.x_array()[:m])); got += m
+    assert got == n and np.array_equal(np.concatenate(xs), back.x_array())
+    r.rewind()
+    assert r.read_chunk(chunk, 10) == 10 and np.array_equal(chunk.x_array()[:10], back.x_array()[:10])
+
+
+def test_las14_format6_records_built_by_hand(pcr, tmp_path):
+    """A LAS 1.4 file with point data record format 6 (30-byte records + 4 bytes of extra data per point),
+    assembled field by field from the ASPRS layout — independent of the writer above."""
+    import struct
+    n = 7
+    X = np.arange(n) * 1000 + 5; Y = np.arange(n) * -250 + 17; Z = np.arange(n) * 10
+    scale, off = (0.01, 0.01, 0.001), (1000.0, -2000.0, 50.0)
+    recs = b""
+    for i in range(n):
+        recs += struct.pack("<iiiHBBBBhHd", int(X[i]), int(Y[i]), int(Z[i]), 100 + i, (i % 15 + 1) | ((15 - i) << 4),
+                            0, 2 + i, 0, -300 + i, 9, 1e5 + i) + b"\xAB\xCD\xEF\x01"
+    head = bytearray(375)
+    head[0:4] = b"LASF"; head[24], head[25] = 1, 4
+    struct.pack_into("<HII", head, 94, 375, 375, 0)
+    head[104] = 6
+    struct.pack_into("<H", head, 105, 34)
+    struct.pack_into("<I", head, 107, 0)                       # legacy count unused in 1.4
+    struct.pack_into("<3d", head, 131, *scale)
+    struct.pack_into("<3d", head, 155, *off)
+    xs, ys = X * scale[0] + off[0], Y * scale[1] + off[1]
+    struct.pack_into("<6d", head, 179, xs.max(), xs.min(), ys.max(), ys.min(), 1.0, 0.0)
+    struct.pack_into("<Q", head, 247, n)
+    path = str(tmp_path / "v14.las")
+    open(path, "wb").write(bytes(head) + recs)
+    info = pcr.read_point_cloud_info(path)
+    assert info.num_points == n and "gps_time" in [c.name for c in info.channels]
+    c = pcr.read_point_cloud(path)
+    assert np.allclose(c.x_array(), xs, rtol=0, atol=1e-9) and np.allclose(c.y_array(), ys, rtol=0, atol=1e-9)
+    assert np.array_equal(c.channel_array_f32("intensity"), 100 + np.arange(n, dtype=np.float32))
+    assert np.array_equal(c.channel_array_f32("classification"), 2 + np.arange(n, dtype=np.float32))
+    assert np.array_equal(c.channel_array_f32("return_number"), (np.arange(n) % 15 + 1).astype(np.float32))
+    assert np.array_equal(c.channel_array_f32("number_of_returns"), (15 - np.arange(n)).astype(np.float32))
+    assert np.allclose(c.channel_array_f32("z"), Z * scale[2] + off[2])
+    # compressed files are refused, not misread
+    bad = bytearray(bytes(head)); bad[104] = 6 | 0x80
+    open(str(tmp_path / "c.las"), "wb").write(bytes(bad) + recs)
+    with pytest.raises(RuntimeError, match="LAZ"):
+        pcr.read_point_cloud_info(str(tmp_path / "c.las"))
+    with pytest.raises(RuntimeError):
+        pcr.read_point_cloud_info(str(tmp_path / "missing.laz"), pcr.PointCloudFormat.LAZ)
