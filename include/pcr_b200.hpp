@@ -500,6 +500,7 @@ struct PipelineConfig {
     int      comm_mode = 0;
     bool     comm_root_only = false;
     bool     async_ingest = false;
+    int      comm_band_copy = 0;
 };
 
 struct ProgressInfo {
@@ -564,6 +565,7 @@ public:
         d.filter = preds.empty() ? nullptr : preds.data();
         d.num_predicates = static_cast<int32_t>(preds.size());
         d.async_ingest = c.async_ingest ? 1 : 0;
+        d.comm_band_copy = c.comm_band_copy;
         if (pcr_pipeline_create(&d, &p->h_) != PCR_OK || !p->h_) {
             const char* m = pcr_last_error();
             std::fprintf(stderr, "Pipeline::create failed: %s\n", m ? m : "");

@@ -325,6 +325,7 @@ Status Engine::init(const pcr_pipeline_desc& d)
     gaussian_variant_ = d.gaussian_kernel;
     comm_mode_ = d.comm_mode;
     gather_root_only_ = d.comm_root_only != 0;
+    band_copy_ = d.comm_band_copy;
     // Ring chunk sizes (points), measured on B200 / PCIe Gen5 x16 with 5M-point ingests: staged (pageable)
     // chunks want to be small so that staging, DMA and kernels overlap early (256 Ki: 2.11 Gpts/s, 2 Mi: 1.85);
     // direct DMA out of pinned caller memory wants few large copies (256 Ki: 2.16, 2 Mi: 2.37).

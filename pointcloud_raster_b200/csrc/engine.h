@@ -226,6 +226,7 @@ private:
     cudaStream_t fin_ = nullptr;
     cudaEvent_t e_pushed_ = nullptr, e_fin_ = nullptr;
     bool fin_pending_ = false;
+    int band_copy_ = 0;               // pcr_pipeline_desc::comm_band_copy
     Status join_fin();                // make the compute stream wait for the last merge/finalize
     // Ingest ring: pinned staging buffers (one staged chunk each) and device buffers (one kernel
     // group each: several staged chunks, or one direct-DMA chunk out of pinned caller memory).

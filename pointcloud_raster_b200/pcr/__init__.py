@@ -697,6 +697,7 @@ class PipelineConfig:
         self.comm_mode = 0
         self.comm_root_only = False
         self.async_ingest = False
+        self.comm_band_copy = 0
 
 
 class ProgressInfo:
@@ -774,6 +775,7 @@ class Pipeline:
         desc.comm_mode = int(getattr(cfg, "comm_mode", 0))
         desc.comm_root_only = int(bool(getattr(cfg, "comm_root_only", False)))
         desc.async_ingest = int(bool(getattr(cfg, "async_ingest", False)))
+        desc.comm_band_copy = int(getattr(cfg, "comm_band_copy", 0))
         preds = list(cfg.filter.predicates)
         if preds:
             arr = (_lib.FilterPredicate * len(preds))()

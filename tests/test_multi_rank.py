@@ -120,7 +120,24 @@ def test_slice_rows_cover_grid(pcr):
 
 
 # ---- the real N>1 path on GPUs ------------------------------------------------------------------
-def _gpu_worker(rank, world, id_path, out_dir, deterministic, comm_mode, overlapped=False):
+def _case(pcr, deterministic, big):
+    """Grid, cloud and reductions shared by the workers and the checker."""
+    from util import make_grid, spec
+    w, h = (350, 260) if big else (300, 211)
+    gc = make_grid(pcr, w, h, tile=64)
+    rng = np.random.default_rng(77)
+    n = 400_000
+    x, y = rng.uniform(-2, w + 2, n), rng.uniform(-2, h * 0.57, n)
+    ch = {"value": rng.normal(0, 3, n).astype(np.float32), "hl": rng.uniform(0, 8, n).astype(np.float32)}
+    R = pcr.ReductionType
+    specs = [spec(pcr, "value", t) for t in (R.Sum, R.Max, R.Min, R.Average, R.Count)]
+    if not deterministic:
+        specs.append(pcr.line_splat_spec("value", default_direction=0.3, half_length_channel="hl", max_radius_cells=9.0))
+        specs.append(pcr.gaussian_splat_spec("value", default_sigma=1.5, max_radius_cells=5.0))
+    return gc, x, y, ch, specs
+
+
+def _gpu_worker(rank, world, id_path, out_dir, deterministic, comm_mode, overlapped=False, big=False):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
     import time
     from pointcloud_raster_b200 import pcr
@@ -131,19 +148,12 @@ def _gpu_worker(rank, world, id_path, out_dir, deterministic, comm_mode, overlap
     while not os.path.exists(id_path):
         time.sleep(0.01)
     uid = open(id_path, "rb").read()
-    gc = make_grid(pcr, 300, 211, tile=64)
-    rng = np.random.default_rng(77)
-    n = 400_000
-    x, y = rng.uniform(-2, 302, n), rng.uniform(-2, 120, n)
-    ch = {"value": rng.normal(0, 3, n).astype(np.float32), "hl": rng.uniform(0, 8, n).astype(np.float32)}
-    R = pcr.ReductionType
-    specs = [spec(pcr, "value", t) for t in (R.Sum, R.Max, R.Min, R.Average, R.Count)]
-    if not deterministic:
-        specs.append(pcr.line_splat_spec("value", default_direction=0.3, half_length_channel="hl", max_radius_cells=9.0))
-        specs.append(pcr.gaussian_splat_spec("value", default_sigma=1.5, max_radius_cells=5.0))
+    gc, x, y, ch, specs = _case(pcr, deterministic, big)
+    n = len(x)
     cfg = pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = specs; cfg.exec_mode = pcr.ExecutionMode.GPU
     cfg.cuda_device_id = rank; cfg.deterministic = deterministic; cfg.comm_mode = comm_mode
     cfg.async_ingest = overlapped
+    cfg.comm_band_copy = 2 if big else 0      # `big` doubles as: ship the bands with the copy engine
     p = pcr.Pipeline.create(cfg)
     assert p is not None
     p.comm_init(uid, rank, world)
@@ -170,6 +180,11 @@ def _gpu_worker(rank, world, id_path, out_dir, deterministic, comm_mode, overlap
 
 
 @pytest.mark.gpu
+def test_multi_gpu_bands_shipped_by_copy_engine(gpu_pcr, oracle):
+    test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, False, 2, overlapped=True, big=True)
+
+
+@pytest.mark.gpu
 def test_multi_gpu_overlapped_steps_match_oracle(gpu_pcr, oracle):
     test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, False, 2, overlapped=True)
 
@@ -177,7 +192,7 @@ def test_multi_gpu_overlapped_steps_match_oracle(gpu_pcr, oracle):
 @pytest.mark.gpu
 @pytest.mark.parametrize("comm_mode", [1, 2], ids=["nccl", "peer"])
 @pytest.mark.parametrize("deterministic", [False, True])
-def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_mode, overlapped=False):
+def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_mode, overlapped=False, big=False):
     if gpu_pcr.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     import multiprocessing as mp
@@ -186,7 +201,7 @@ def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_
     world = min(gpu_pcr.device_count(), 4)
     ctx = mp.get_context("spawn")
     with tempfile.TemporaryDirectory() as d:
-        procs = [ctx.Process(target=_gpu_worker, args=(r, world, os.path.join(d, "id"), d, deterministic, comm_mode, overlapped))
+        procs = [ctx.Process(target=_gpu_worker, args=(r, world, os.path.join(d, "id"), d, deterministic, comm_mode, overlapped, big))
                  for r in range(world)]
         for pr in procs: pr.start()
         for pr in procs: pr.join(300)
@@ -199,16 +214,7 @@ def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_
         for a, b in zip(per_rank[0], per_rank[r]):
             assert np.array_equal(a, b, equal_nan=True)
     pcr = gpu_pcr
-    gc = make_grid(pcr, 300, 211, tile=64)
-    rng = np.random.default_rng(77)
-    n = 400_000
-    x, y = rng.uniform(-2, 302, n), rng.uniform(-2, 120, n)
-    ch = {"value": rng.normal(0, 3, n).astype(np.float32), "hl": rng.uniform(0, 8, n).astype(np.float32)}
-    R = pcr.ReductionType
-    specs = [spec(pcr, "value", t) for t in (R.Sum, R.Max, R.Min, R.Average, R.Count)]
-    if not deterministic:
-        specs.append(pcr.line_splat_spec("value", default_direction=0.3, half_length_channel="hl", max_radius_cells=9.0))
-        specs.append(pcr.gaussian_splat_spec("value", default_sigma=1.5, max_radius_cells=5.0))
+    gc, x, y, ch, specs = _case(pcr, deterministic, big)
     gd = grid_desc(gc)
     ref = oracle.run(gd, [(x, y, ch)], specs)
     compare_bands(oracle, gd, [(x, y, ch)], specs, ref, per_rank[0], f"{world} GPUs", device_weights=True)
