@@ -125,10 +125,8 @@ typedef struct pcr_pipeline_desc {
                                                        stream sync; buffers must stay valid until the
                                                        next finalize / synchronize */
     int32_t                   comm_band_copy;       /* N>1 peer mode, how a rank's finalized band slice reaches
-                                                       the other ranks: 0 = auto (copy engine when the slice is
-                                                       >= 4 MB per band and >= 3 ranks converge on a receiver,
-                                                       else stores from the merge kernel), 1 = kernel stores,
-                                                       2 = copy engine */
+                                                       the other ranks: 0/1 = stores from the merge kernel
+                                                       (default), 2 = one copy-engine transfer per band and peer */
 } pcr_pipeline_desc;
 
 /* One named channel of a point cloud (pcr::PointCloud, include/pcr/core/point_cloud.h:29-103). */

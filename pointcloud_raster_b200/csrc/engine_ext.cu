@@ -359,17 +359,16 @@ Status Engine::finalize_multi_peer()
     for (size_t i = 0; i < reductions_.size(); ++i)
         if (reductions_[i].rejected)
             CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), fin_));
-    // Where do my slice's bands go besides my own array?  Small slices are stored straight into the peers'
-    // arrays by the merge kernel (one NVLink latency, no extra launch).  Large slices are written locally
-    // and shipped with one copy-engine transfer per band and peer: seven ranks' 128-byte stores converging
-    // on rank 0 were measured at 230 GB/s (config 5 on 8 GPUs: 18 ms for 4.2 GB).
+    // Where do my slice's bands go besides my own array?  By default the merge kernel stores them straight
+    // into the peers' arrays (one NVLink latency, no extra launch, overlapped with the merge itself).
+    // comm_band_copy = 2 writes them locally and ships one copy-engine transfer per band and peer instead.
+    // Measured on config 5 (20000 x 20000, 1B points): no gain at 8 GPUs (rank 0 takes in 5.6 GB of
+    // records + 4.2 GB of bands either way, 18 ms at its ~0.6 TB/s NVLink ingress) and a loss at 2 GPUs
+    // (the copy only starts after the merge: 14.0 -> 17.1 ms), so it is opt-in.
     std::vector<int> targets;
     for (int k = 0; k < world_; ++k)
         if (k != rank_ && !(gather_root_only_ && k != 0)) targets.push_back(k);
-    // (with a single sender there is no convergence to relieve, and the copy only delays the bands:
-    //  config 5 on 2 GPUs 14.0 -> 17.1 ms)
-    const bool bulk_bands = band_copy_ == 2 ||
-                            (band_copy_ == 0 && world_ >= 4 && my_cells * sizeof(float) >= (size_t(4) << 20));
+    const bool bulk_bands = band_copy_ == 2;
     OutTargets outs{};
     outs.out[outs.n++] = d_out_;
     if (!bulk_bands)
