@@ -254,6 +254,10 @@ const char *pcr_geotiff_last_error(void);
  * ordered on); end records a second one, synchronizes and returns the elapsed ms. */
 int pcr_pipeline_timer_begin(pcr_pipeline *p);
 int pcr_pipeline_timer_end(pcr_pipeline *p, double *elapsed_ms);
+/* Per-kernel-group CUDA events.  on = 0: off; 1: every kernel group; N > 1: every Nth group of each kind
+ * (accumulate, sort, push, finalize, init) — two timed events around a 60 us kernel cost ~5 us of stream
+ * time and keep the next kernel from launching under its tail, so a hot loop samples.  The `*_launches`
+ * fields of pcr_profile count the SAMPLED groups (mean = *_ms / *_launches); `kernel_launches` counts all. */
 int pcr_pipeline_profile_enable(pcr_pipeline *p, int32_t on);
 int pcr_pipeline_profile_reset(pcr_pipeline *p);
 int pcr_pipeline_profile_read(pcr_pipeline *p, pcr_profile *out);

@@ -224,7 +224,7 @@ int pcr_pipeline_load_state(pcr_pipeline* p, const char* dir)
 int pcr_pipeline_reset(pcr_pipeline* p) { NEED(p); return finish(eng(p)->reset()); }
 int pcr_pipeline_synchronize(pcr_pipeline* p) { NEED(p); return finish(eng(p)->synchronize()); }
 
-int pcr_pipeline_profile_enable(pcr_pipeline* p, int32_t on) { NEED(p); return finish(eng(p)->profile_enable(on != 0)); }
+int pcr_pipeline_profile_enable(pcr_pipeline* p, int32_t on) { NEED(p); return finish(eng(p)->profile_enable(on < 0 ? 0 : on)); }
 int pcr_pipeline_profile_reset(pcr_pipeline* p) { NEED(p); return finish(eng(p)->profile_reset()); }
 int pcr_pipeline_profile_read(pcr_pipeline* p, pcr_profile* out)
 {

@@ -567,7 +567,8 @@ Status Engine::validate() const
 // ---------------------------------------------------------------------------
 void Engine::prof_begin(ProfKind k, cudaStream_t s)
 {
-    if (!prof_on_) return;
+    prof_cur_ = {nullptr, nullptr, k};
+    if (!prof_on_ || (prof_seq_[k]++ % static_cast<uint64_t>(prof_on_)) != 0) return;   // not sampled
     auto get = [&]() {
         cudaEvent_t e;
         if (!prof_free_.empty()) { e = prof_free_.back(); prof_free_.pop_back(); }
@@ -580,10 +581,11 @@ void Engine::prof_begin(ProfKind k, cudaStream_t s)
 
 void Engine::prof_end(cudaStream_t s)
 {
-    if (!prof_on_) return;
+    if (!prof_cur_.a) return;
     cudaEventRecord(prof_cur_.b, s);
     prof_open_.push_back(prof_cur_);
     ++prof_n_[prof_cur_.k];
+    prof_cur_.a = nullptr;
 }
 
 Status Engine::prof_collect()
@@ -600,7 +602,13 @@ Status Engine::prof_collect()
     return Status::success();
 }
 
-Status Engine::profile_enable(bool on) { CU_TRY(cudaSetDevice(device_)); prof_on_ = on; return Status::success(); }
+Status Engine::profile_enable(int period)
+{
+    CU_TRY(cudaSetDevice(device_));
+    prof_on_ = period;
+    for (auto& q : prof_seq_) q = 0;
+    return Status::success();
+}
 
 Status Engine::profile_reset()
 {

@@ -149,7 +149,7 @@ public:
     Status load_state(const std::string& dir);
     Status synchronize();
 
-    Status profile_enable(bool on);
+    Status profile_enable(int period);      // 0 = off, N = sample every Nth kernel group of each kind
     Status profile_reset();
     Status profile_read(pcr_profile& out);
     Status timer_begin();
@@ -268,7 +268,8 @@ private:
     void* progress_user_ = nullptr;
 
     // ---- profiling ----
-    bool prof_on_ = false;
+    int prof_on_ = 0;                       // sampling period, 0 = off
+    uint64_t prof_seq_[8] = {};             // kernel groups seen per kind
     struct ProfSpan { cudaEvent_t a, b; ProfKind k; };
     std::vector<ProfSpan> prof_open_;
     std::vector<cudaEvent_t> prof_free_;

@@ -933,7 +933,8 @@ class Pipeline:
         check(lib.pcr_pipeline_synchronize(self._h))
 
     def profile_enable(self, on=True):
-        check(lib.pcr_pipeline_profile_enable(self._h, int(bool(on))))
+        """on: False/0 = off, True/1 = time every kernel group, N > 1 = every Nth group of each kind."""
+        check(lib.pcr_pipeline_profile_enable(self._h, int(on)))
 
     def profile_reset(self):
         check(lib.pcr_pipeline_profile_reset(self._h))
