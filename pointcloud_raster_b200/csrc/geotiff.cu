@@ -23,6 +23,8 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 
 namespace pcrb {
@@ -133,36 +135,69 @@ extern "C" int pcr_geotiff_write(const char* path, const float* const* bands, in
     std::fwrite(hdr.data(), 1, hdr.size(), f);
     uint64_t pos = hdr.size();
 
-    // tiles, band after band
+    // tiles, band after band.  Gathering (and DEFLATE) of the tiles is spread over worker threads that claim
+    // tile indices from an atomic cursor and fill a ring of slots; this thread writes the slots to the file in
+    // tile order.  (zlib level 6 on float data runs at ~17 MB/s per core: one 1000 x 1000 band took 236 ms
+    // single-threaded.)
     std::vector<uint64_t> tile_off, tile_len;
-    std::vector<float> tile(static_cast<size_t>(tw) * th);
-    std::vector<uint8_t> zbuf(compression == 8 ? compressBound(raw_tile) : 0);
+    const size_t total_tiles = per_band * static_cast<size_t>(num_bands);
     const float nan = std::numeric_limits<float>::quiet_NaN();
-    bool io_ok = true;
-    for (int b = 0; b < num_bands && io_ok; ++b) {
+    const int level = std::max(1, std::min(9, compress_level));
+    const size_t zcap = compression == 8 ? compressBound(raw_tile) : 0;
+    struct Slot { std::vector<float> tile; std::vector<uint8_t> z; size_t len = 0; std::atomic<uint64_t> ready{0}; };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    // uncompressed small rasters are a few memcpys: not worth starting threads for
+    const bool threaded = compression == 8 || static_cast<double>(total_tiles) * raw_tile >= 64e6;
+    const size_t n_workers = threaded ? std::min<size_t>({size_t(hw), size_t(16), total_tiles}) : 1;
+    const size_t n_slots = std::max<size_t>(2, n_workers * 2);
+    std::vector<Slot> slots(n_slots);
+    for (Slot& sl : slots) { sl.tile.resize(static_cast<size_t>(tw) * th); sl.z.resize(zcap); }
+    std::atomic<size_t> cursor{0}, written{0};
+    std::atomic<bool> failed{false};
+    auto produce = [&](size_t t) {                               // tile t -> slot t % n_slots
+        Slot& sl = slots[t % n_slots];
+        while (t >= written.load(std::memory_order_acquire) + n_slots && !failed.load()) std::this_thread::yield();
+        const int b = static_cast<int>(t / per_band);
+        const size_t r = t % per_band;
+        const int ty = static_cast<int>(r / tiles_x), tx = static_cast<int>(r % tiles_x);
         const float* src = bands[b];
-        for (int ty = 0; ty < tiles_y && io_ok; ++ty)
-            for (int tx = 0; tx < tiles_x && io_ok; ++tx) {
-                const int x0 = tx * tw, y0 = ty * th;
-                const int cw = std::min(tw, W - x0), chh = std::min(th, H - y0);
-                if (cw < tw || chh < th) std::fill(tile.begin(), tile.end(), nan);
-                for (int r = 0; r < chh; ++r)
-                    std::memcpy(&tile[static_cast<size_t>(r) * tw], src + static_cast<size_t>(y0 + r) * W + x0,
-                                static_cast<size_t>(cw) * sizeof(float));
-                const void* out = tile.data();
-                uint64_t len = raw_tile;
-                if (compression == 8) {
-                    uLongf zl = zbuf.size();
-                    if (compress2(zbuf.data(), &zl, reinterpret_cast<const Bytef*>(tile.data()), raw_tile,
-                                  std::max(1, std::min(9, compress_level))) != Z_OK) { io_ok = false; break; }
-                    out = zbuf.data(); len = zl;
-                }
-                tile_off.push_back(pos); tile_len.push_back(len);
-                io_ok = std::fwrite(out, 1, len, f) == len;
-                pos += len;
-                if (pos & 1) { std::fputc(0, f); ++pos; }          // word alignment
-            }
+        const int x0 = tx * tw, y0 = ty * th;
+        const int cw = std::min(tw, W - x0), chh = std::min(th, H - y0);
+        if (cw < tw || chh < th) std::fill(sl.tile.begin(), sl.tile.end(), nan);
+        for (int row = 0; row < chh; ++row)
+            std::memcpy(&sl.tile[static_cast<size_t>(row) * tw], src + static_cast<size_t>(y0 + row) * W + x0,
+                        static_cast<size_t>(cw) * sizeof(float));
+        sl.len = raw_tile;
+        if (compression == 8) {
+            uLongf zl = sl.z.size();
+            if (compress2(sl.z.data(), &zl, reinterpret_cast<const Bytef*>(sl.tile.data()), raw_tile, level) != Z_OK)
+                failed.store(true);
+            sl.len = zl;
+        }
+        sl.ready.store(t + 1, std::memory_order_release);
+    };
+    std::vector<std::thread> workers;
+    for (size_t w = 0; w + 1 < n_workers; ++w)
+        workers.emplace_back([&] {
+            for (size_t t; (t = cursor.fetch_add(1)) < total_tiles && !failed.load();) produce(t);
+        });
+    bool io_ok = true;
+    for (size_t t = 0; t < total_tiles; ++t) {
+        Slot& sl = slots[t % n_slots];
+        if (workers.empty()) produce(cursor.fetch_add(1));       // single-core box: do it here
+        while (sl.ready.load(std::memory_order_acquire) != t + 1 && !failed.load()) std::this_thread::yield();
+        if (failed.load()) { io_ok = false; break; }
+        const void* out = compression == 8 ? static_cast<const void*>(sl.z.data()) : static_cast<const void*>(sl.tile.data());
+        tile_off.push_back(pos); tile_len.push_back(sl.len);
+        if (io_ok) io_ok = std::fwrite(out, 1, sl.len, f) == sl.len;
+        pos += sl.len;
+        if (pos & 1) { std::fputc(0, f); ++pos; }                  // word alignment
+        written.store(t + 1, std::memory_order_release);
+        if (!io_ok) { failed.store(true); break; }
     }
+    if (!io_ok) failed.store(true);
+    written.store(total_tiles + n_slots, std::memory_order_release);   // release any waiting producer
+    for (auto& w : workers) w.join();
     if (!io_ok) { std::fclose(f); return fail(PCR_IO_ERROR, "failed to write band data"); }
 
     // tags
