@@ -140,3 +140,19 @@ def test_live_differential_glyphs(oracle, seed):
     ref = orc.reference_run(gd, [(x, y, ch)], specs)
     got = oracle.run(gd, [(x, y, ch)], specs)
     _compare(oracle, gd, [(x, y, ch)], specs, ref, got, f"live glyph seed {seed}")
+
+
+@needs_ref
+def test_live_differential_random_configs(oracle, pcr):
+    """The 96 seeded random pipelines of tests/test_random_configs_gpu.py (awkward cell sizes, far origins,
+    tiny reference tiles, points on every edge, NaN / inf coordinates and values, Line and Gaussian glyphs
+    with per-point channels) through the UNMODIFIED reference and through the C oracle: the same cases the
+    CUDA path is held to on the GPU box are first used to pin the oracle itself."""
+    import test_random_configs_gpu as cases
+    from util import compare_bands, grid_desc
+    for seed in range(96):
+        gc, clouds, specs, _knobs, _loc = cases._random_case(pcr, seed)
+        gd = grid_desc(gc)
+        ref = orc.reference_run(gd, clouds, specs)
+        got = oracle.run(gd, clouds, specs)
+        compare_bands(oracle, gd, clouds, specs, ref, got, f"reference vs oracle, seed {seed}")
