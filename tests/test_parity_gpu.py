@@ -475,3 +475,33 @@ def test_config5_like_large_grid(gpu_pcr):
     touched = np.zeros((5, 5), bool)
     touched[np.minimum(row // 4096, 4), np.minimum(col // 4096, 4)] = True
     assert p.stats().tiles_active == int(touched.sum())
+
+
+# ---- independent pipelines from several host threads (the reference's ThreadSafety_ConcurrentAccess idea) ----
+def test_independent_pipelines_in_parallel_threads(gpu_pcr, oracle):
+    import threading
+    gc = make_grid(gpu_pcr, 220, 170, tile=64)
+    gd = grid_desc(gc)
+    R = gpu_pcr.ReductionType
+    results, errors = {}, []
+
+    def work(tid):
+        try:
+            x, y, ch = uniform_cloud(120_000, 220, 170, seed=100 + tid, margin=-1.0)
+            ch["sigma"] = np.full(len(x), 1.5 + tid, np.float32)
+            specs = [spec(gpu_pcr, "value", R.Sum), spec(gpu_pcr, "value", R.Max), spec(gpu_pcr, "value", R.Count),
+                     gpu_pcr.gaussian_splat_spec("value", "sigma", "sigma", max_radius_cells=12.0)]
+            for rep in range(3):                                  # pipelines are created and torn down concurrently
+                got, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs,
+                                     loc=[None, gpu_pcr.MemoryLocation.HostPinned, gpu_pcr.MemoryLocation.Device][rep])
+            results[tid] = ((x, y, ch), specs, got)
+        except Exception as e:          # noqa
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not errors, errors
+    for tid, (cl, specs, got) in results.items():
+        ref = oracle.run(gd, [cl], specs)
+        compare_bands(oracle, gd, [cl], specs, ref, got, f"thread {tid}", device_weights=True)
