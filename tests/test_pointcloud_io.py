@@ -195,3 +195,51 @@ def test_las14_format6_records_built_by_hand(pcr, tmp_path):
         pcr.read_point_cloud_info(str(tmp_path / "c.las"))
     with pytest.raises(RuntimeError):
         pcr.read_point_cloud_info(str(tmp_path / "missing.laz"), pcr.PointCloudFormat.LAZ)
+
+
+@pytest.mark.gpu
+def test_las_ground_points_to_dem(gpu_pcr, tmp_path):
+    """The LiDAR use case of the reference's scripts/data/test_dc_lidar.py: a LAS tile streamed into the
+    pipeline, ground returns only (classification == 2, FilterSpec on the device), z -> Max/Average/Count."""
+    pcr = gpu_pcr
+    from util import make_grid, spec
+    rng = np.random.default_rng(12)
+    n = 60_000
+    x = np.round(rng.uniform(323000.0, 323100.0, n), 3)
+    y = np.round(rng.uniform(4306000.0, 4306080.0, n), 3)
+    z = np.round(rng.uniform(5, 60, n), 3)
+    cls = rng.choice([1, 2, 5, 6], n).astype(np.float32)
+    c = pcr.PointCloud.create(n); c.set_x_array(x); c.set_y_array(y)
+    for k, v in (("z", z), ("classification", cls), ("intensity", rng.integers(0, 4000, n))):
+        c.add_channel(k, pcr.DataType.Float32); c.set_channel_array_f32(k, np.asarray(v, np.float32))
+    path = str(tmp_path / "tile.las")
+    pcr.write_point_cloud(path, c, pcr.PointCloudFormat.LAS)
+
+    cfg = pcr.PipelineConfig()
+    cfg.grid = make_grid(pcr, 100, 80, cell=2.0, min_x=323000.0, min_y=4306000.0)
+    cfg.exec_mode = pcr.ExecutionMode.GPU
+    cfg.filter.add("classification", pcr.CompareOp.Equal, 2.0)
+    cfg.reductions = [spec(pcr, "z", pcr.ReductionType.Max), spec(pcr, "z", pcr.ReductionType.Average),
+                      spec(pcr, "z", pcr.ReductionType.Count)]
+    p = pcr.Pipeline.create(cfg)
+    r = pcr.PointCloudReader.open(path)
+    chunk = pcr.PointCloud.create(8192, pcr.MemoryLocation.HostPinned)
+    while not r.eof():
+        r.read_chunk(chunk, 8192)
+        p.ingest(chunk)
+    p.finalize()
+    back = pcr.read_point_cloud(path)
+    bx, by = np.array(back.x_array()), np.array(back.y_array())
+    bz, bc = np.array(back.channel_array_f32("z")), np.array(back.channel_array_f32("classification"))
+    g = bc == 2
+    col = np.minimum(np.floor((bx[g] - 323000.0) / 2.0).astype(int), 49)
+    row = np.minimum(np.floor((by[g] - 4306080.0) / -2.0).astype(int), 39)
+    cnt = np.zeros((40, 50)); np.add.at(cnt, (row, col), 1)
+    mx = np.full((40, 50), -np.inf, np.float32); np.maximum.at(mx, (row, col), bz[g])
+    sm = np.zeros((40, 50)); np.add.at(sm, (row, col), bz[g].astype(np.float64))
+    got = [np.array(p.result().band_array(i)) for i in range(3)]
+    assert p.stats().points_processed == int(g.sum())
+    has = cnt > 0
+    assert np.array_equal(np.isnan(got[2]), ~has) and np.array_equal(got[2][has], cnt[has].astype(np.float32))
+    assert np.array_equal(got[0][has], mx[has])
+    assert np.allclose(got[1][has], (sm[has] / cnt[has]), rtol=1e-5, atol=0)
