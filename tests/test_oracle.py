@@ -156,3 +156,36 @@ def test_live_differential_random_configs(oracle, pcr):
         ref = orc.reference_run(gd, clouds, specs)
         got = oracle.run(gd, clouds, specs)
         compare_bands(oracle, gd, clouds, specs, ref, got, f"reference vs oracle, seed {seed}")
+
+
+@needs_ref
+def test_live_differential_world_to_cell(pcr):
+    """GridConfig.compute_dimensions / world_to_cell of the product library against the reference's own, on
+    awkward cell sizes, far origins, exact cell boundaries, both inclusive edges and their neighbours, NaN / inf."""
+    ref = orc.load_reference(False)
+    rng = np.random.default_rng(0)
+    checked = 0
+    for _ in range(40):
+        cs = float(rng.choice([1.0, 0.5, 0.1, 0.3, 2.7, 1e-3, 1e3, 7.0]))
+        csy = -cs * float(rng.choice([1.0, 0.5, 3.0]))
+        ox = float(rng.choice([0.0, -1e6 + 0.3, 4.5e6 + 0.1, 12.5]))
+        oy = float(rng.choice([0.0, 7e5 + 0.7, -33.25]))
+        w, h = int(rng.integers(1, 500)), int(rng.integers(1, 500))
+        g, r = pcr.GridConfig(), ref.GridConfig()
+        for c in (g, r):
+            c.bounds.min_x, c.bounds.min_y = ox, oy
+            c.bounds.max_x, c.bounds.max_y = ox + w * cs, oy + h * abs(csy)
+            c.cell_size_x, c.cell_size_y = cs, csy
+            c.compute_dimensions()
+        assert (g.width, g.height, g.tiles_x, g.tiles_y) == (r.width, r.height, r.tiles_x, r.tiles_y)
+        xs = np.concatenate([rng.uniform(ox - cs, ox + (w + 1) * cs, 200), ox + cs * rng.integers(0, w + 1, 60),
+                             [ox, ox + w * cs, np.nextafter(ox, -np.inf), np.nextafter(ox + w * cs, np.inf),
+                              np.nan, np.inf, -np.inf, -0.0]])
+        ys = np.concatenate([rng.uniform(oy - cs, oy + (h + 1) * abs(csy), 200), oy + abs(csy) * rng.integers(0, h + 1, 60),
+                             [oy, g.bounds.max_y, np.nextafter(oy, -np.inf), np.nextafter(g.bounds.max_y, np.inf),
+                              np.nan, np.inf, -np.inf, 0.0]])
+        for x, y in zip(xs, rng.permutation(ys)):
+            a, b = g.world_to_cell(float(x), float(y)), r.world_to_cell(float(x), float(y))
+            assert bool(a[2]) == bool(b[2]) and (not a[2] or (a[0], a[1]) == (b[0], b[1])), (cs, csy, ox, oy, x, y, a, b)
+            checked += 1
+    assert checked > 10000
