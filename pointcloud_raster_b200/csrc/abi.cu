@@ -4,6 +4,8 @@
 
 #include <cmath>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 
 using pcrb::Engine;
 using pcrb::Status;
@@ -21,6 +23,25 @@ int fail(int code, const char* msg)
     g_last_error = msg;
     return code;
 }
+// No C++ exception may cross the extern "C" boundary (a bad_alloc unwinding through ctypes / a C caller
+// aborts the host process): every entry that reaches the engine runs under this guard.
+template <typename F>
+int guarded(F&& f) noexcept
+{
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        return fail(PCR_OUT_OF_MEMORY, "out of host memory");
+    } catch (const std::length_error&) {
+        return fail(PCR_OUT_OF_MEMORY, "out of host memory (allocation size overflow)");
+    } catch (const std::exception& e) {
+        g_last_error = std::string("internal error: ") + e.what();
+        return PCR_IO_ERROR;
+    } catch (...) {
+        return fail(PCR_IO_ERROR, "internal error: unknown exception");
+    }
+}
+#define GUARD(expr) guarded([&]() -> int { return (expr); })
 Engine* eng(pcr_pipeline* p) { return reinterpret_cast<Engine*>(p); }
 const Engine* eng(const pcr_pipeline* p) { return reinterpret_cast<const Engine*>(p); }
 }  // namespace
@@ -147,17 +168,22 @@ int pcr_pipeline_create(const pcr_pipeline_desc* desc, pcr_pipeline** out)
     if (!desc) return fail(PCR_INVALID_ARGUMENT, "pcr_pipeline_create: null desc");
     if (desc->num_reductions < 0 || (desc->num_reductions > 0 && !desc->reductions))
         return fail(PCR_INVALID_ARGUMENT, "pcr_pipeline_create: bad reductions array");
-    Engine* e = nullptr;
-    Status s = Engine::create(*desc, &e);
-    *out = reinterpret_cast<pcr_pipeline*>(e);
-    return finish(s);
+    return guarded([&]() -> int {
+        Engine* e = nullptr;
+        Status s = Engine::create(*desc, &e);
+        *out = reinterpret_cast<pcr_pipeline*>(e);
+        return finish(s);
+    });
 }
 
-void pcr_pipeline_destroy(pcr_pipeline* p) { delete eng(p); }
+void pcr_pipeline_destroy(pcr_pipeline* p)
+{
+    try { delete eng(p); } catch (...) {}
+}
 
 #define NEED(p) if (!(p)) return fail(PCR_INVALID_ARGUMENT, "null pipeline handle")
 
-int pcr_pipeline_validate(const pcr_pipeline* p) { NEED(p); return finish(eng(p)->validate()); }
+int pcr_pipeline_validate(const pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->validate())); }
 
 int pcr_pipeline_ingest(pcr_pipeline* p, const double* x, const double* y, size_t count,
                         const pcr_channel_view* channels, int32_t num_channels, int32_t location)
@@ -165,41 +191,43 @@ int pcr_pipeline_ingest(pcr_pipeline* p, const double* x, const double* y, size_
     NEED(p);
     if (num_channels < 0 || (num_channels > 0 && !channels))
         return fail(PCR_INVALID_ARGUMENT, "pcr_pipeline_ingest: bad channel array");
-    return finish(eng(p)->ingest(x, y, count, channels, num_channels, location));
+    return GUARD(finish(eng(p)->ingest(x, y, count, channels, num_channels, location)));
 }
 
-int pcr_pipeline_finalize(pcr_pipeline* p) { NEED(p); return finish(eng(p)->finalize(true)); }
-int pcr_pipeline_finalize_device(pcr_pipeline* p) { NEED(p); return finish(eng(p)->finalize(false)); }
+int pcr_pipeline_finalize(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->finalize(true))); }
+int pcr_pipeline_finalize_device(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->finalize(false))); }
 
 int pcr_pipeline_result_band(pcr_pipeline* p, int32_t band, const float** data, int32_t* rows, int32_t* cols)
 {
     NEED(p);
     if (!data || !rows || !cols) return fail(PCR_INVALID_ARGUMENT, "null output pointer");
-    return finish(eng(p)->result_band(band, data, rows, cols, false));
+    return GUARD(finish(eng(p)->result_band(band, data, rows, cols, false)));
 }
 
 int pcr_pipeline_result_band_device(pcr_pipeline* p, int32_t band, const float** data, int32_t* rows, int32_t* cols)
 {
     NEED(p);
     if (!data || !rows || !cols) return fail(PCR_INVALID_ARGUMENT, "null output pointer");
-    return finish(eng(p)->result_band(band, data, rows, cols, true));
+    return GUARD(finish(eng(p)->result_band(band, data, rows, cols, true)));
 }
 
 int pcr_pipeline_band_name(const pcr_pipeline* p, int32_t band, char* buf, size_t buflen)
 {
     NEED(p);
     if (!buf || !buflen) return fail(PCR_INVALID_ARGUMENT, "null buffer");
-    std::string name;
-    Status s = eng(p)->band_name(band, name);
-    if (s.ok()) std::snprintf(buf, buflen, "%s", name.c_str());
-    return finish(s);
+    return guarded([&]() -> int {
+        std::string name;
+        Status s = eng(p)->band_name(band, name);
+        if (s.ok()) std::snprintf(buf, buflen, "%s", name.c_str());
+        return finish(s);
+    });
 }
 
 int pcr_pipeline_stats(const pcr_pipeline* p, pcr_progress* out)
 {
     NEED(p);
     if (!out) return fail(PCR_INVALID_ARGUMENT, "null output pointer");
-    return finish(const_cast<Engine*>(eng(p))->stats(*out));
+    return GUARD(finish(const_cast<Engine*>(eng(p))->stats(*out)));
 }
 
 int pcr_pipeline_set_progress_callback(pcr_pipeline* p, pcr_progress_fn fn, void* user)
@@ -213,38 +241,38 @@ int pcr_pipeline_save_state(pcr_pipeline* p, const char* dir)
 {
     NEED(p);
     if (!dir || !dir[0]) return fail(PCR_INVALID_ARGUMENT, "pcr_pipeline_save_state: empty directory");
-    return finish(eng(p)->save_state(dir));
+    return GUARD(finish(eng(p)->save_state(dir)));
 }
 int pcr_pipeline_load_state(pcr_pipeline* p, const char* dir)
 {
     NEED(p);
     if (!dir || !dir[0]) return fail(PCR_INVALID_ARGUMENT, "pcr_pipeline_load_state: empty directory");
-    return finish(eng(p)->load_state(dir));
+    return GUARD(finish(eng(p)->load_state(dir)));
 }
-int pcr_pipeline_reset(pcr_pipeline* p) { NEED(p); return finish(eng(p)->reset()); }
-int pcr_pipeline_synchronize(pcr_pipeline* p) { NEED(p); return finish(eng(p)->synchronize()); }
+int pcr_pipeline_reset(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->reset())); }
+int pcr_pipeline_synchronize(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->synchronize())); }
 
-int pcr_pipeline_profile_enable(pcr_pipeline* p, int32_t on) { NEED(p); return finish(eng(p)->profile_enable(on < 0 ? 0 : on)); }
-int pcr_pipeline_profile_reset(pcr_pipeline* p) { NEED(p); return finish(eng(p)->profile_reset()); }
+int pcr_pipeline_profile_enable(pcr_pipeline* p, int32_t on) { NEED(p); return GUARD(finish(eng(p)->profile_enable(on < 0 ? 0 : on))); }
+int pcr_pipeline_profile_reset(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->profile_reset())); }
 int pcr_pipeline_profile_read(pcr_pipeline* p, pcr_profile* out)
 {
     NEED(p);
     if (!out) return fail(PCR_INVALID_ARGUMENT, "null output pointer");
-    return finish(eng(p)->profile_read(*out));
+    return GUARD(finish(eng(p)->profile_read(*out)));
 }
 
-int pcr_pipeline_timer_begin(pcr_pipeline* p) { NEED(p); return finish(eng(p)->timer_begin()); }
+int pcr_pipeline_timer_begin(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->timer_begin())); }
 int pcr_pipeline_timer_end(pcr_pipeline* p, double* elapsed_ms)
 {
     NEED(p);
     if (!elapsed_ms) return fail(PCR_INVALID_ARGUMENT, "null output pointer");
-    return finish(eng(p)->timer_end(*elapsed_ms));
+    return GUARD(finish(eng(p)->timer_end(*elapsed_ms)));
 }
 
 int pcr_comm_unique_id(void* id128)
 {
     if (!id128) return fail(PCR_INVALID_ARGUMENT, "null id buffer");
-    return finish(pcrb::comm_unique_id(id128));
+    return GUARD(finish(pcrb::comm_unique_id(id128)));
 }
 
 int pcr_comm_slice_rows(int32_t height, int32_t world_size, int32_t rank, int32_t* row0, int32_t* row1)
@@ -259,9 +287,9 @@ int pcr_pipeline_comm_init(pcr_pipeline* p, const void* id128, int32_t rank, int
 {
     NEED(p);
     if (!id128 && world_size > 1) return fail(PCR_INVALID_ARGUMENT, "null id buffer");
-    return finish(eng(p)->comm_init(id128, rank, world_size));
+    return GUARD(finish(eng(p)->comm_init(id128, rank, world_size)));
 }
 
-int pcr_pipeline_comm_barrier(pcr_pipeline* p) { NEED(p); return finish(eng(p)->comm_barrier()); }
+int pcr_pipeline_comm_barrier(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->comm_barrier())); }
 
 }  // extern "C"

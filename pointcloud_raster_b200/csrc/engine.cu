@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <emmintrin.h>
+#include <sched.h>
 
 namespace pcrb {
 
@@ -25,6 +26,20 @@ namespace pcrb {
     } while (0)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Host copy threads of the pageable staging path: up to 12 (measured optimum on a 16-core host for one
+// GPU), but never more than this rank's share of the cores this process may run on — N ranks with 12
+// spinning workers each on a 32-core host made the pageable path slower in aggregate at N=8 than at N=1.
+int default_staging_threads(int local_ranks)
+{
+    const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+    unsigned mine = cores;                                   // cores this process may run on
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) mine = static_cast<unsigned>(std::max(1, CPU_COUNT(&set)));
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) local_ranks = std::max(local_ranks, std::atoi(e));
+    const unsigned share = std::min(mine, std::max(1u, cores / static_cast<unsigned>(std::max(1, local_ranks))));
+    return static_cast<int>(std::max(1u, std::min(12u, share > 1 ? share - 1 : 1u)));   // one core stays with the ingesting thread
+}
 
 // ---------------------------------------------------------------------------
 // CopyPool
@@ -335,8 +350,8 @@ Status Engine::init(const pcr_pipeline_desc& d)
     const int depth = d.ring_depth > 0 ? d.ring_depth : 3;
     host_ring_.resize(depth);
     dev_ring_.resize(std::max(depth, 2));
-    staging_threads_ = d.staging_threads > 0 ? d.staging_threads
-                                             : std::max(1u, std::min(12u, std::thread::hardware_concurrency()));
+    staging_auto_ = d.staging_threads <= 0;
+    staging_threads_ = d.staging_threads > 0 ? d.staging_threads : default_staging_threads(1);
 
     if (exec_mode_ == PCR_EXEC_CPU)
         return Status::error(PCR_NOT_IMPLEMENTED,
@@ -540,8 +555,11 @@ Engine::~Engine()
     for (auto& ev : prof_free_) cudaEventDestroy(ev);
     if (timer_a_) { cudaEventDestroy(timer_a_); cudaEventDestroy(timer_b_); }
     delete pool_;
+    if (e_pushed_) cudaEventDestroy(e_pushed_);
+    if (e_fin_) cudaEventDestroy(e_fin_);
     if (compute_) cudaStreamDestroy(compute_);
     if (copy_) cudaStreamDestroy(copy_);
+    if (fin_) cudaStreamDestroy(fin_);
 }
 
 // Pipeline::validate, src/engine/pipeline.cpp:1306-1338
@@ -1105,15 +1123,14 @@ Status Engine::stats(pcr_progress& o)
     o.collections_processed = collections_;
     o.collections_total = 0;
     o.points_processed = points_;
-    if (d_survivors_) {
-        unsigned long long kept = 0;
+    // both read-backs ride one stream sync (the progress callback calls this after every ingest)
+    unsigned long long kept = 0;
+    if (d_survivors_)
         CU_TRY(cudaMemcpyAsync(&kept, d_survivors_, sizeof kept, cudaMemcpyDeviceToHost, compute_));
-        CU_TRY(cudaStreamSynchronize(compute_));
-        o.points_processed += kept;
-    }
     std::vector<uint32_t> t(std::max(1, n_tiles_));
     CU_TRY(cudaMemcpyAsync(t.data(), d_touched_, t.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, compute_));
     CU_TRY(cudaStreamSynchronize(compute_));
+    o.points_processed += kept;
     uint64_t active = 0;
     for (int i = 0; i < n_tiles_; ++i) active += t[i] ? 1 : 0;
     o.tiles_active = active;

@@ -249,6 +249,7 @@ private:
     size_t slot_bytes_ = 0;
     CopyPool* pool_ = nullptr;
     int staging_threads_ = 0;
+    bool staging_auto_ = true;       // not set by the caller: re-derived from the local world size at comm_init
     Status ensure_ring();
 
     // deterministic-mode scratch
@@ -311,6 +312,7 @@ cudaError_t det_point_reduce(cudaStream_t s, const uint32_t* keys, const uint32_
                              const ChannelPtrs& ch, uint32_t* state, const PassLayout& L,
                              uint32_t invalid_key);
 Status comm_unique_id(void* id128);
+int default_staging_threads(int local_ranks);
 // rows [row0,row1) owned by `rank`: ceil(height/world) rows each, the last slices may be short or empty
 inline void slice_rows(int height, int world, int rank, int& row0, int& row1)
 {

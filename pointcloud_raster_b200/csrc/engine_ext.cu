@@ -171,6 +171,7 @@ Status Engine::comm_init(const void* id128, int rank, int world)
     NC_TRY(nccl_->CommInitRank(&comm_, world, id, rank));
     rank_ = rank;
     world_ = world;
+    if (staging_auto_ && !pool_) staging_threads_ = default_staging_threads(world);   // ranks share one host
     CU_TRY(cudaMalloc(&d_touched_all_, std::max(1, n_tiles_) * sizeof(uint32_t)));
     if (comm_mode_ != 1) {
         Status s = peer_map();
