@@ -116,8 +116,9 @@ typedef struct pcr_pipeline_desc {
                                                        2 = gather (tile-binned, atomic-free, deterministic) */
     int32_t                   comm_mode;            /* N>1 combine: 0 = auto (peer memory over NVLink when every
                                                        GPU pair has P2P access, else NCCL), 1 = NCCL, 2 = peer */
-    int32_t                   comm_root_only;       /* 1 = only rank 0 ends with complete bands (other ranks
-                                                       keep their own row slice) */
+    int32_t                   comm_root_only;       /* N>1, where the finalized bands end up: 0 = complete on every
+                                                       rank, 1 = complete on rank 0 only, 2 = distributed (every
+                                                       rank holds just the row slice it owns, pcr_comm_slice_rows) */
     const pcr_filter_predicate *filter;             /* PipelineConfig::filter (N3): evaluated on the device,
                                                        fused in front of routing; NULL/0 = no filter */
     int32_t                   num_predicates;
@@ -192,7 +193,10 @@ void pcr_pipeline_destroy(pcr_pipeline *p);
 int pcr_pipeline_validate(const pcr_pipeline *p);
 /* Pipeline::ingest -> Impl::process_cloud, src/engine/pipeline.cpp:283-770,1340.
  * Borrowed pointers; `location` says where x/y/channels live (host pageable, host
- * pinned or device).  Returns once the caller may free or overwrite the buffers. */
+ * pinned or device).  Returns once the caller may free or overwrite the buffers.
+ * PCR_MEM_DEVICE buffers are read by kernels on the pipeline's own (non-blocking) stream: they must be
+ * COMPLETE before the call — synchronize the stream that produced them (the legacy default stream
+ * included); there is no implicit ordering against the caller's streams. */
 int pcr_pipeline_ingest(pcr_pipeline *p, const double *x, const double *y, size_t count,
                         const pcr_channel_view *channels, int32_t num_channels,
                         int32_t location);
@@ -261,6 +265,14 @@ int pcr_pipeline_timer_end(pcr_pipeline *p, double *elapsed_ms);
 int pcr_pipeline_profile_enable(pcr_pipeline *p, int32_t on);
 int pcr_pipeline_profile_reset(pcr_pipeline *p);
 int pcr_pipeline_profile_read(pcr_pipeline *p, pcr_profile *out);
+
+/* Measurement aid (not on the product path): median time, in microseconds over `reps` launches, of folding
+ * `points` synthetic points with hashed cells into `cells` 16-byte records [sum, count, max, pad] with the
+ * reduction instructions of the Point kernel (one red.global.add.v2.f32 + one red.global.max.s32 per point),
+ * optionally behind the kernel's three streaming loads per point (x, y f64 + value f32).  This is the rate at
+ * which the GPU's L2 resolves scattered reductions — the ceiling bench.py quotes next to the HBM roofline. */
+int pcr_diag_red_ceiling(int device, uint64_t points, uint64_t cells, int with_loads, int reps,
+                         double *median_us);
 
 /* ---- multi-GPU: one process per GPU, point shards, combine at finalize ----- */
 /* The partial grid states of all ranks are merged with Op::merge semantics

@@ -121,6 +121,7 @@ SYMBOLS = [
     ("pcr_pipeline_profile_read", C.c_int, [C.c_void_p, C.POINTER(Profile)]),
     ("pcr_pipeline_timer_begin", C.c_int, [C.c_void_p]),
     ("pcr_pipeline_timer_end", C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    ("pcr_diag_red_ceiling", C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("pcr_comm_unique_id", C.c_int, [C.c_void_p]),
     ("pcr_comm_slice_rows", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("pcr_pipeline_comm_init", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

@@ -339,7 +339,8 @@ Status Engine::init(const pcr_pipeline_desc& d)
     warp_aggregate_ = d.warp_aggregate != 2;
     gaussian_variant_ = d.gaussian_kernel;
     comm_mode_ = d.comm_mode;
-    gather_root_only_ = d.comm_root_only != 0;
+    gather_root_only_ = d.comm_root_only == 1;
+    bands_distributed_ = d.comm_root_only == 2;
     band_copy_ = d.comm_band_copy;
     // Ring chunk sizes (points), measured on B200 / PCIe Gen5 x16 with 5M-point ingests: staged (pageable)
     // chunks want to be small so that staging, DMA and kernels overlap early (256 Ki: 2.11 Gpts/s, 2 Mi: 1.85);
@@ -465,9 +466,12 @@ Status Engine::init(const pcr_pipeline_desc& d)
 
 Status Engine::alloc_state()
 {
-    for (Pass& p : passes_)
-        CU_TRY(cudaMalloc(&p.d_state, cells_ * p.layout.width * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&d_touched_, std::max(1, n_tiles_) * sizeof(uint32_t)));
+    for (Pass& p : passes_) {
+        CU_TRY(cudaMalloc(&p.d_delta[0], cells_ * p.layout.width * sizeof(uint32_t)));
+        p.d_state = p.d_delta[0];
+    }
+    CU_TRY(cudaMalloc(&d_touched_buf_[0], std::max(1, n_tiles_) * sizeof(uint32_t)));
+    d_touched_ = d_touched_buf_[0];
     const size_t out_bytes = std::max<size_t>(1, reductions_.size()) * cells_ * sizeof(float);
     CU_TRY(cudaMalloc(&d_out_, out_bytes));
     if (!filter_.empty()) {
@@ -484,8 +488,19 @@ Status Engine::alloc_state()
 Status Engine::init_state()
 {
     prof_begin(PROF_INIT, compute_);
-    for (Pass& p : passes_) { CU_TRY(launch_init_state(compute_, p.d_state, cells_, p.layout)); ++launches_; }
-    CU_TRY(cudaMemsetAsync(d_touched_, 0, std::max(1, n_tiles_) * sizeof(uint32_t), compute_));
+    for (Pass& p : passes_) {
+        for (uint32_t* d : p.d_delta)
+            if (d) { CU_TRY(launch_init_state(compute_, d, cells_, p.layout)); ++launches_; }
+        if (p.d_owned) {
+            int r0, r1;
+            slice_rows(grid_.height, world_, rank_, r0, r1);
+            CU_TRY(launch_init_state(compute_, p.d_owned, static_cast<size_t>(r1 - r0) * grid_.width, p.layout));
+            ++launches_;
+        }
+    }
+    for (uint32_t* t : d_touched_buf_)
+        if (t) CU_TRY(cudaMemsetAsync(t, 0, std::max(1, n_tiles_) * sizeof(uint32_t), compute_));
+    if (d_touched_merged_) CU_TRY(cudaMemsetAsync(d_touched_merged_, 0, std::max(1, n_tiles_) * sizeof(uint32_t), compute_));
     prof_end(compute_);
     return Status::success();
 }
@@ -530,8 +545,10 @@ Engine::~Engine()
     }
     peer_unmap();
     if (comm_) engine_comm_destroy(nccl_, comm_);
-    for (Pass& p : passes_) { cudaFree(p.d_state); cudaFree(p.d_combined); }
-    cudaFree(d_touched_);
+    for (Pass& p : passes_) { cudaFree(p.d_delta[0]); cudaFree(p.d_delta[1]); cudaFree(p.d_owned); cudaFree(p.d_combined); }
+    cudaFree(d_touched_buf_[0]);
+    cudaFree(d_touched_buf_[1]);
+    if (e_delta_) cudaEventDestroy(e_delta_);
     cudaFree(d_touched_all_);
     cudaFree(d_touched_merged_);
     cudaFree(d_flags_);
@@ -1127,12 +1144,18 @@ Status Engine::stats(pcr_progress& o)
     unsigned long long kept = 0;
     if (d_survivors_)
         CU_TRY(cudaMemcpyAsync(&kept, d_survivors_, sizeof kept, cudaMemcpyDeviceToHost, compute_));
-    std::vector<uint32_t> t(std::max(1, n_tiles_));
-    CU_TRY(cudaMemcpyAsync(t.data(), d_touched_, t.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, compute_));
+    // delta mode: the tiles touched so far = those of the delta in progress, of a push still in flight,
+    // and everything the ranks have merged at earlier finalizes
+    const size_t nt = std::max(1, n_tiles_);
+    const uint32_t* srcs[3] = {d_touched_buf_[0], d_touched_buf_[1], d_touched_merged_};
+    std::vector<uint32_t> t(3 * nt, 0);
+    if (delta_mode_) ST_TRY(join_fin());
+    for (int k = 0; k < 3; ++k)
+        if (srcs[k]) CU_TRY(cudaMemcpyAsync(t.data() + k * nt, srcs[k], nt * sizeof(uint32_t), cudaMemcpyDeviceToHost, compute_));
     CU_TRY(cudaStreamSynchronize(compute_));
     o.points_processed += kept;
     uint64_t active = 0;
-    for (int i = 0; i < n_tiles_; ++i) active += t[i] ? 1 : 0;
+    for (int i = 0; i < n_tiles_; ++i) active += (t[i] | t[nt + i] | t[2 * nt + i]) ? 1 : 0;
     o.tiles_active = active;
     o.elapsed_seconds = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0_).count();
     return Status::success();

@@ -64,8 +64,13 @@ struct Pass {
     PassLayout layout{};
     FinalizeProgram fin{};
     std::vector<std::string> channels;   // distinct value channels, index = ChannelPtrs slot
-    uint32_t* d_state = nullptr;         // cells * layout.width words
+    uint32_t* d_state = nullptr;         // cells * layout.width words: what the accumulate kernels update
     uint32_t* d_combined = nullptr;      // multi-GPU: received peer slices
+    // multi-GPU peer mode ("delta epochs"): d_state alternates between two full-grid DELTA buffers — the
+    // ingests since the previous finalize — while the push of the other one is still in flight; the rank
+    // that owns a row slice keeps the running merge of everybody's deltas in d_owned.
+    uint32_t* d_delta[2] = {nullptr, nullptr};
+    uint32_t* d_owned = nullptr;         // my row slice, accumulated over all finalizes so far
 };
 
 // Worker pool for the pageable -> pinned staging copies of one host ingest.
@@ -178,6 +183,7 @@ private:
     Status finalize_multi_peer();
     Status peer_map();               // exchange CUDA IPC handles, map every rank's buffers
     void peer_unmap();
+    void peer_close_handles();
     int channel_slot(const std::string& name);
 
     // profiling helpers
@@ -212,7 +218,11 @@ private:
     // ---- plan / state ----
     std::vector<Pass> passes_;
     std::vector<std::string> all_channels_;   // every channel any pass reads (value + glyph)
-    uint32_t* d_touched_ = nullptr;
+    uint32_t* d_touched_ = nullptr;           // what the accumulate kernels set (= d_touched_buf_[cur_])
+    uint32_t* d_touched_buf_[2] = {nullptr, nullptr};
+    bool delta_mode_ = false;                 // peer mode: states and touched flags are per-finalize deltas
+    int cur_ = 0;
+    cudaEvent_t e_delta_ = nullptr;           // compute stream: the delta of this epoch is complete
     uint32_t* d_touched_all_ = nullptr;       // multi-GPU merged flags
     uint32_t* d_touched_merged_ = nullptr;   // peer mode: OR of every rank's touched-tile flags
     float* d_out_ = nullptr;                  // [bands][cells]
@@ -288,6 +298,7 @@ private:
     bool peer_ok_ = false;
     int comm_mode_ = 0;               // 0 auto (peer memory when every pair has P2P), 1 NCCL, 2 peer
     bool gather_root_only_ = false;
+    bool bands_distributed_ = false;  // N>1: every rank keeps only its own row slice of the bands
     struct PeerBuffers {
         std::vector<uint32_t*> combined;   // one per pass: kMaxParts slots of max_slice cells
         uint32_t* touched_stage = nullptr; // [world][n_tiles]

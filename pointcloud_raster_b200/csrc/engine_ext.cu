@@ -181,60 +181,108 @@ Status Engine::comm_init(const void* id128, int rank, int world)
 }
 
 // ---------------------------------------------------------------------------
-// Peer-memory path: map every rank's state / touched / band / flag buffers with CUDA IPC so
-// that the merge+finalize kernel reads the peers' partial records straight over NVLink and
-// stores the finalized slice straight into the peers' band arrays — no staging buffer, no
-// separate collective.  NCCL is used once, to all-gather the 64-byte IPC handles.
+// Peer-memory path: map every rank's combine / touched-staging / band / flag buffers with CUDA IPC so
+// that the push kernel stores partial records straight into their owner's memory over NVLink and the
+// merge+finalize kernel stores the finalized slice straight into the peers' band arrays — no staging
+// buffer, no separate collective.  NCCL is used once, to all-gather the 64-byte IPC handles.
 // ---------------------------------------------------------------------------
 Status Engine::peer_map()
 {
     peer_ok_ = false;
-    // all ranks must agree: 1 iff this rank can reach every other device
+    int* d_flag = nullptr;
+    CU_TRY(cudaMalloc(&d_flag, sizeof(int) * std::max(world_, 2)));
+    // every rank must reach every collective below whatever happens locally: failures are recorded and
+    // agreed on by an all-reduce(min) instead of returning early (a rank that left would hang the others)
+    auto agree = [&](int mine, int& all) -> Status {
+        CU_TRY(cudaMemcpyAsync(d_flag, &mine, sizeof(int), cudaMemcpyHostToDevice, compute_));
+        NC_TRY(nccl_->AllReduce(d_flag, d_flag, 1, NcclApi::kUint32, /*ncclMin*/ 3, comm_, compute_));
+        CU_TRY(cudaMemcpyAsync(&all, d_flag, sizeof(int), cudaMemcpyDeviceToHost, compute_));
+        CU_TRY(cudaStreamSynchronize(compute_));
+        return Status::success();
+    };
+    struct FreeFlag { int* p; ~FreeFlag() { cudaFree(p); } } free_flag{d_flag};
+
+    // 1. can this rank reach every other device?
     int can_all = 1;
-    std::vector<int> devs(world_, 0);
     {
-        int* d_dev = nullptr;
-        CU_TRY(cudaMalloc(&d_dev, sizeof(int) * world_));
-        CU_TRY(cudaMemcpyAsync(d_dev + rank_, &device_, sizeof(int), cudaMemcpyHostToDevice, compute_));
-        NC_TRY(nccl_->AllGather(d_dev + rank_, d_dev, sizeof(int), NcclApi::kUint8, comm_, compute_));
-        CU_TRY(cudaMemcpyAsync(devs.data(), d_dev, sizeof(int) * world_, cudaMemcpyDeviceToHost, compute_));
+        std::vector<int> devs(world_, 0);
+        CU_TRY(cudaMemcpyAsync(d_flag + rank_, &device_, sizeof(int), cudaMemcpyHostToDevice, compute_));
+        NC_TRY(nccl_->AllGather(d_flag + rank_, d_flag, sizeof(int), NcclApi::kUint8, comm_, compute_));
+        CU_TRY(cudaMemcpyAsync(devs.data(), d_flag, sizeof(int) * world_, cudaMemcpyDeviceToHost, compute_));
         CU_TRY(cudaStreamSynchronize(compute_));
         for (int k = 0; k < world_; ++k) {
             if (k == rank_) continue;
             int ok = 0;
             if (devs[k] == device_ || cudaDeviceCanAccessPeer(&ok, device_, devs[k]) != cudaSuccess || !ok) can_all = 0;
         }
-        CU_TRY(cudaMemcpyAsync(d_dev, &can_all, sizeof(int), cudaMemcpyHostToDevice, compute_));
-        NC_TRY(nccl_->AllReduce(d_dev, d_dev, 1, NcclApi::kUint32, /*ncclMin*/ 3, comm_, compute_));
-        CU_TRY(cudaMemcpyAsync(&can_all, d_dev, sizeof(int), cudaMemcpyDeviceToHost, compute_));
-        CU_TRY(cudaStreamSynchronize(compute_));
-        cudaFree(d_dev);
+        cudaGetLastError();
     }
-    if (!can_all)
+    int all_can = 0;
+    ST_TRY(agree(can_all, all_can));
+    if (!all_can)
         return Status::error(PCR_CUDA_ERROR, "pipeline: peer-memory combine needs P2P access between all ranks' GPUs");
 
-    if (!d_flags_) {
-        CU_TRY(cudaMalloc(&d_flags_, (2 * kMaxParts + 4) * sizeof(uint32_t)));   // + the done counter
-        CU_TRY(cudaMemsetAsync(d_flags_, 0, (2 * kMaxParts + 4) * sizeof(uint32_t), compute_));
-    }
-    // combine buffers (the push targets) and touched staging, one slot per rank
+    // 2. local buffers: combine buffers (the push targets), the second delta buffer, the owner slice,
+    //    touched staging; one ok flag for all of them
     const size_t rows_per = (static_cast<size_t>(grid_.height) + world_ - 1) / world_;
     const size_t max_slice = rows_per * static_cast<size_t>(grid_.width);
-    for (Pass& p : passes_)
-        if (!p.d_combined)
-            CU_TRY(cudaMalloc(&p.d_combined, static_cast<size_t>(world_) * max_slice * p.layout.width * 4));
-    if (!d_touched_merged_) CU_TRY(cudaMalloc(&d_touched_merged_, std::max(1, n_tiles_) * sizeof(uint32_t)));
-    if (!d_touched_stage_) {
-        CU_TRY(cudaMalloc(&d_touched_stage_, static_cast<size_t>(world_) * std::max(1, n_tiles_) * 4));
-        CU_TRY(cudaMemsetAsync(d_touched_stage_, 0, static_cast<size_t>(world_) * std::max(1, n_tiles_) * 4, compute_));
-    }
-    // handles: [pass combine buffers..., touched staging, out, flags]
+    const size_t nt = std::max(1, n_tiles_);
+    int r0, r1;
+    slice_rows(grid_.height, world_, rank_, r0, r1);
+    const size_t my_cells = static_cast<size_t>(r1 - r0) * grid_.width;
+    auto alloc_local = [&]() -> Status {
+        if (!d_flags_) {
+            CU_TRY(cudaMalloc(&d_flags_, (2 * kMaxParts + 4) * sizeof(uint32_t)));   // + the done counter
+            CU_TRY(cudaMemsetAsync(d_flags_, 0, (2 * kMaxParts + 4) * sizeof(uint32_t), compute_));
+        }
+        for (Pass& p : passes_) {
+            const size_t W = p.layout.width;
+            if (!p.d_combined) CU_TRY(cudaMalloc(&p.d_combined, static_cast<size_t>(world_) * max_slice * W * 4));
+            if (!p.d_delta[1]) {
+                CU_TRY(cudaMalloc(&p.d_delta[1], cells_ * W * 4));
+                CU_TRY(launch_init_state(compute_, p.d_delta[1], cells_, p.layout));
+            }
+            if (!p.d_owned) {
+                CU_TRY(cudaMalloc(&p.d_owned, std::max<size_t>(my_cells, 1) * W * 4));
+                CU_TRY(launch_init_state(compute_, p.d_owned, my_cells, p.layout));
+            }
+        }
+        if (!d_touched_buf_[1]) {
+            CU_TRY(cudaMalloc(&d_touched_buf_[1], nt * 4));
+            CU_TRY(cudaMemsetAsync(d_touched_buf_[1], 0, nt * 4, compute_));
+        }
+        if (!d_touched_merged_) {
+            CU_TRY(cudaMalloc(&d_touched_merged_, nt * 4));
+            CU_TRY(cudaMemsetAsync(d_touched_merged_, 0, nt * 4, compute_));
+        }
+        if (!d_touched_stage_) {
+            CU_TRY(cudaMalloc(&d_touched_stage_, static_cast<size_t>(world_) * nt * 4));
+            CU_TRY(cudaMemsetAsync(d_touched_stage_, 0, static_cast<size_t>(world_) * nt * 4, compute_));
+        }
+        if (!e_delta_) CU_TRY(cudaEventCreateWithFlags(&e_delta_, cudaEventDisableTiming));
+        return Status::success();
+    };
+    Status local = alloc_local();
+    if (!local.ok()) cudaGetLastError();
+
+    // 3. handles: [pass combine buffers..., touched staging, out, flags]
     const size_t n_buf = passes_.size() + 3;
     std::vector<cudaIpcMemHandle_t> mine(n_buf);
-    for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(cudaIpcGetMemHandle(&mine[i], passes_[i].d_combined));
-    CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size()], d_touched_stage_));
-    CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 1], d_out_));
-    CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 2], d_flags_));
+    if (local.ok()) {
+        auto get = [&]() -> Status {
+            for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(cudaIpcGetMemHandle(&mine[i], passes_[i].d_combined));
+            CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size()], d_touched_stage_));
+            CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 1], d_out_));
+            CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 2], d_flags_));
+            return Status::success();
+        };
+        local = get();
+    }
+    int all_local = 0;
+    ST_TRY(agree(local.ok() ? 1 : 0, all_local));
+    if (!all_local)
+        return local.ok() ? Status::error(PCR_CUDA_ERROR, "pipeline: a peer rank could not allocate its combine buffers") : local;
+
     const size_t bytes = n_buf * sizeof(cudaIpcMemHandle_t);
     std::vector<cudaIpcMemHandle_t> all(n_buf * world_);
     unsigned char* d_h = nullptr;
@@ -245,28 +293,52 @@ Status Engine::peer_map()
     CU_TRY(cudaStreamSynchronize(compute_));
     cudaFree(d_h);
 
-    for (int k = 0; k < world_; ++k) {
-        PeerBuffers& pb = peer_[k];
-        pb.combined.assign(passes_.size(), nullptr);
-        if (k == rank_) {
-            for (size_t i = 0; i < passes_.size(); ++i) pb.combined[i] = passes_[i].d_combined;
-            pb.touched_stage = d_touched_stage_; pb.out = d_out_; pb.flags = d_flags_;
-            continue;
+    // 4. open the peers' buffers; on any failure everyone closes what it opened and falls back together
+    auto open_all = [&]() -> Status {
+        for (int k = 0; k < world_; ++k) {
+            PeerBuffers& pb = peer_[k];
+            pb = PeerBuffers{};
+            pb.combined.assign(passes_.size(), nullptr);
+            if (k == rank_) {
+                for (size_t i = 0; i < passes_.size(); ++i) pb.combined[i] = passes_[i].d_combined;
+                pb.touched_stage = d_touched_stage_; pb.out = d_out_; pb.flags = d_flags_;
+                continue;
+            }
+            const cudaIpcMemHandle_t* h = &all[n_buf * k];
+            auto open = [&](const cudaIpcMemHandle_t& hh, void** out) {
+                return cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess);
+            };
+            for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(open(h[i], reinterpret_cast<void**>(&pb.combined[i])));
+            CU_TRY(open(h[passes_.size()], reinterpret_cast<void**>(&pb.touched_stage)));
+            CU_TRY(open(h[passes_.size() + 1], reinterpret_cast<void**>(&pb.out)));
+            CU_TRY(open(h[passes_.size() + 2], reinterpret_cast<void**>(&pb.flags)));
         }
-        const cudaIpcMemHandle_t* h = &all[n_buf * k];
-        auto open = [&](const cudaIpcMemHandle_t& hh, void** out) {
-            return cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess);
-        };
-        for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(open(h[i], reinterpret_cast<void**>(&pb.combined[i])));
-        CU_TRY(open(h[passes_.size()], reinterpret_cast<void**>(&pb.touched_stage)));
-        CU_TRY(open(h[passes_.size() + 1], reinterpret_cast<void**>(&pb.out)));
-        CU_TRY(open(h[passes_.size() + 2], reinterpret_cast<void**>(&pb.flags)));
+        return Status::success();
+    };
+    Status opened = open_all();
+    if (!opened.ok()) cudaGetLastError();
+    int all_open = 0;
+    ST_TRY(agree(opened.ok() ? 1 : 0, all_open));     // also: nobody signals into a flag array that is not zeroed yet
+    if (!all_open) {
+        peer_close_handles();
+        return opened.ok() ? Status::error(PCR_CUDA_ERROR, "pipeline: a peer rank could not map the combine buffers") : opened;
     }
-    // nobody may signal into a flag array that is not zeroed yet / unmap-safe start
-    NC_TRY(nccl_->AllReduce(d_touched_all_, d_touched_all_, 1, NcclApi::kUint32, NcclApi::kMax, comm_, compute_));
-    CU_TRY(cudaStreamSynchronize(compute_));
     peer_ok_ = true;
+    delta_mode_ = true;
     return Status::success();
+}
+
+void Engine::peer_close_handles()
+{
+    for (int k = 0; k < world_; ++k) {
+        if (k == rank_) continue;
+        for (uint32_t* p : peer_[k].combined) if (p) cudaIpcCloseMemHandle(p);
+        if (peer_[k].touched_stage) cudaIpcCloseMemHandle(peer_[k].touched_stage);
+        if (peer_[k].out) cudaIpcCloseMemHandle(peer_[k].out);
+        if (peer_[k].flags) cudaIpcCloseMemHandle(peer_[k].flags);
+        peer_[k] = PeerBuffers{};
+    }
+    cudaGetLastError();
 }
 
 void Engine::peer_unmap()
@@ -277,13 +349,7 @@ void Engine::peer_unmap()
         nccl_->AllReduce(d_touched_all_, d_touched_all_, 1, NcclApi::kUint32, NcclApi::kMax, comm_, compute_);
         cudaStreamSynchronize(compute_);
     }
-    for (int k = 0; k < world_; ++k) {
-        if (k == rank_) continue;
-        for (uint32_t* p : peer_[k].combined) if (p) cudaIpcCloseMemHandle(p);
-        if (peer_[k].touched_stage) cudaIpcCloseMemHandle(peer_[k].touched_stage);
-        if (peer_[k].out) cudaIpcCloseMemHandle(peer_[k].out);
-        if (peer_[k].flags) cudaIpcCloseMemHandle(peer_[k].flags);
-    }
+    peer_close_handles();
     if (comm_ && nccl_) {   // ... and every mapping must be closed before the owners free the memory
         nccl_->AllReduce(d_touched_all_, d_touched_all_, 1, NcclApi::kUint32, NcclApi::kMax, comm_, compute_);
         cudaStreamSynchronize(compute_);
@@ -291,22 +357,28 @@ void Engine::peer_unmap()
     peer_ok_ = false;
 }
 
-// N>1 finalize over peer memory.  No host sync anywhere; two streams.
-// Compute stream (behind the ingest kernels):
-//   k_peer_wait     one small kernel: the peers are done reading their combine buffers (phase 1 of
-//                   the previous epoch)
-//   k_push_slices   persistent copy kernel: every record is stored into the combine buffer of the rank
-//                   that owns its row (posted NVLink writes; a local copy for my own slice), my
-//                   touched-tile flags into everyone's staging; the last CTA releases phase 0 on every rank.
-//                   After it the live state is free again: the next ingest's kernels start right here.
-// Finalize stream (highest priority, forked from the compute stream after the push):
-//   k_peer_wait_merge_touched   one small kernel: every rank's push has landed here; OR the touched flags
-//   k_finalize_peer persistent kernel: merges the `world` parts of my slice in rank order (Op::merge),
-//                   finalizes, stores the bands into my array and the peers' arrays; the last CTA
-//                   releases phase 1
+// N>1 finalize over peer memory, "delta epochs".  No host sync anywhere; two streams.
+//
+// What a rank accumulates between two finalizes is a DELTA (records start from the identity); the rank
+// that owns a row slice keeps the running merge of everybody's deltas (d_owned).  Because Op::merge is
+// a commutative monoid (builtin_ops.h:15,28,41,54,67,95-97) the result is the same state a single
+// cumulative grid would hold, and the delta buffers are double-buffered, so NOTHING of a finalize sits
+// on the ingest stream: the kernels of the next ingest start at once, into the other delta buffer.
+//
+// Compute stream: [ingest kernels of epoch e] -> event "delta e complete" -> [ingest kernels of e+1 ...]
+// Finalize stream (highest priority), behind that event:
+//   k_peer_wait     the peers are done reading their combine buffers (phase 1 of epoch e-1)
+//   k_push_slices   persistent copy kernel: every record of the delta goes into the combine buffer of the
+//                   rank that owns its row (posted NVLink writes; a local copy for my own slice) and is put
+//                   back to the identity behind the copy; my touched-tile flags go into everyone's staging;
+//                   the last CTA releases phase 0 on every rank
+//   k_peer_wait_merge_touched   every rank's push has landed here; OR the touched flags into the merged set
+//   k_finalize_peer persistent kernel: owned = merge(owned, delta of rank 0, 1, ...) in rank order, finalize,
+//                   store the bands into my array and the peers' arrays; the last CTA releases phase 1
 //   (k_peer_wait)   peer_quiesce(): phase 1 from everyone, before the host reads the bands.
-// The compute stream re-joins the finalize stream only where it must: before the next push (my own
-// combine buffer), before a D2H of the bands, in synchronize() and in timer_end().
+// The compute stream waits for the finalize stream only where it must: before it accumulates into the
+// delta buffer whose push was enqueued one finalize earlier, before a D2H of the bands, in synchronize()
+// and in timer_end().
 Status Engine::finalize_multi_peer()
 {
     ++epoch_;
@@ -325,35 +397,41 @@ Status Engine::finalize_multi_peer()
     slice_rows(grid_.height, world_, rank_, r0, r1);
     const size_t my0 = static_cast<size_t>(r0) * grid_.width, my_cells = static_cast<size_t>(r1 - r0) * grid_.width;
 
-    // ---- compute stream: snapshot every slice into its owner's combine buffer ----
-    ST_TRY(join_fin());     // my previous merge still reads my own combine buffer
+    // ---- compute stream: the delta of this epoch is complete; flip to the other buffer ----
+    const int old = cur_;
+    CU_TRY(cudaEventRecord(e_delta_, compute_));
+    // the other buffer was pushed (and reset) by the previous finalize: its push must be done before the
+    // next ingest accumulates into it (in steady state that event is long past)
+    if (epoch_ > 1) CU_TRY(cudaStreamWaitEvent(compute_, e_pushed_, 0));
+    cur_ ^= 1;
+    for (Pass& p : passes_) p.d_state = p.d_delta[cur_];
+    d_touched_ = d_touched_buf_[cur_];
+
+    // ---- finalize stream: push the delta, wait for the peers' pushes, merge, finalize, store the bands ----
+    CU_TRY(cudaStreamWaitEvent(fin_, e_delta_, 0));
+    ps.waited = 1;
+    prof_begin(PROF_PUSH, fin_);
     // The peers' combine buffers may still be read by their previous merge: one small kernel waits for
     // their "done" flags of the previous epoch (instead of every CTA of the push polling them).
-    ps.waited = 1;
-    prof_begin(PROF_PUSH, compute_);
-    if (epoch_ > 1) { CU_TRY(launch_peer_wait(compute_, ps.pf, 1, epoch_ - 1)); ++launches_; }
-    if (passes_.empty()) CU_TRY(launch_peer_signal(compute_, ps.pf, 0, epoch_));
+    if (epoch_ > 1) { CU_TRY(launch_peer_wait(fin_, ps.pf, 1, epoch_ - 1)); ++launches_; }
+    if (passes_.empty()) CU_TRY(launch_peer_signal(fin_, ps.pf, 0, epoch_));
     for (size_t i = 0; i < passes_.size(); ++i) {
         PushTargets pt{};
         for (int k = 0; k < world_; ++k) { pt.combined[k] = peer_[k].combined[i]; pt.touched_stage[k] = peer_[k].touched_stage; }
         pt.rows_per = static_cast<int>(rows_per);
         pt.max_slice_cells = max_slice;
-        CU_TRY(launch_push_slices(compute_, passes_[i].d_state, d_touched_, n_tiles_, gp_, passes_[i].layout, pt, ps,
-                                  i == 0, i + 1 == passes_.size(), sm_count_));
+        CU_TRY(launch_push_slices(fin_, passes_[i].d_delta[old], d_touched_buf_[old], n_tiles_, gp_, passes_[i].layout, pt, ps,
+                                  i + 1 == passes_.size(), i + 1 == passes_.size(), true, sm_count_));
         ++launches_;
     }
-    prof_end(compute_);
-    CU_TRY(cudaEventRecord(e_pushed_, compute_));
+    prof_end(fin_);
+    CU_TRY(cudaEventRecord(e_pushed_, fin_));
 
-    // ---- finalize stream: wait for the peers' pushes, merge in rank order, finalize, store the bands.
-    //      Nothing below reads the live state (the push snapshotted this rank's own slice as well),
-    //      so the kernels of the next ingest run on the compute stream while this waits on NVLink.
-    CU_TRY(cudaStreamWaitEvent(fin_, e_pushed_, 0));
     prof_begin(PROF_FIN, fin_);
     // One small kernel holds the stream until every peer's push has landed (the merge kernel's own CTAs
     // would all spin on the same flags and occupy the SMs the next ingest wants) and ORs the ranks'
-    // touched-tile flags into one array.
-    CU_TRY(launch_peer_wait_merge_touched(fin_, ps.pf, epoch_, ps.pt, d_touched_merged_, std::max(1, n_tiles_)));
+    // touched-tile flags into the merged set.
+    CU_TRY(launch_peer_wait_merge_touched(fin_, ps.pf, epoch_, ps.pt, d_touched_merged_, std::max(1, n_tiles_), true));
     ++launches_;
     ps.pt.n = 1;
     ps.pt.touched[0] = d_touched_merged_;
@@ -362,13 +440,11 @@ Status Engine::finalize_multi_peer()
             CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), fin_));
     // Where do my slice's bands go besides my own array?  By default the merge kernel stores them straight
     // into the peers' arrays (one NVLink latency, no extra launch, overlapped with the merge itself).
-    // comm_band_copy = 2 writes them locally and ships one copy-engine transfer per band and peer instead.
-    // Measured on config 5 (20000 x 20000, 1B points): no gain at 8 GPUs (rank 0 takes in 5.6 GB of
-    // records + 4.2 GB of bands either way, 18 ms at its ~0.6 TB/s NVLink ingress) and a loss at 2 GPUs
-    // (the copy only starts after the merge: 14.0 -> 17.1 ms), so it is opt-in.
+    // comm_band_copy = 2 writes them locally and ships one copy-engine transfer per band and peer instead
+    // (measured on config 5 in round 1: no gain at 8 GPUs, a loss at 2), so it is opt-in.
     std::vector<int> targets;
     for (int k = 0; k < world_; ++k)
-        if (k != rank_ && !(gather_root_only_ && k != 0)) targets.push_back(k);
+        if (k != rank_ && !(gather_root_only_ && k != 0) && !bands_distributed_) targets.push_back(k);
     const bool bulk_bands = band_copy_ == 2;
     OutTargets outs{};
     outs.out[outs.n++] = d_out_;
@@ -379,11 +455,12 @@ Status Engine::finalize_multi_peer()
         Pass& p = passes_[i];
         const size_t W = p.layout.width;
         StateParts parts{};
-        parts.n = world_;
-        for (int k = 0; k < world_; ++k) parts.part[k] = p.d_combined + static_cast<size_t>(k) * max_slice * W;
+        parts.n = world_ + 1;
+        parts.part[0] = p.d_owned;
+        for (int k = 0; k < world_; ++k) parts.part[k + 1] = p.d_combined + static_cast<size_t>(k) * max_slice * W;
         ps.signal_begin = 0;
         ps.signal_end = !bulk_bands && i + 1 == passes_.size();
-        CU_TRY(launch_finalize_peer(fin_, parts, my0, my0, my_cells, outs, cells_, gp_, p.layout, p.fin, ps, sm_count_));
+        CU_TRY(launch_finalize_peer(fin_, parts, my0, my0, my_cells, outs, cells_, gp_, p.layout, p.fin, ps, p.d_owned, sm_count_));
         ++launches_;
     }
     if (bulk_bands) {
@@ -398,9 +475,8 @@ Status Engine::finalize_multi_peer()
     prof_end(fin_);
     CU_TRY(cudaEventRecord(e_fin_, fin_));
     fin_pending_ = true;
-    // Not awaited here: the peers' "done" flags of this epoch.  They are awaited by the next push kernel
-    // (before it overwrites the peers' combine buffers) and by peer_quiesce() before the host looks at
-    // the bands.
+    // Not awaited here: the peers' "done" flags of this epoch.  They are awaited by the next push (before
+    // it overwrites the peers' combine buffers) and by peer_quiesce() before the host looks at the bands.
     return Status::success();
 }
 

@@ -21,7 +21,7 @@ struct GlyphParams {
 // (multi-GPU combine; 1 part on a single GPU).
 constexpr int kMaxParts = 8;
 struct StateParts {
-    const uint32_t* part[kMaxParts];
+    const uint32_t* part[kMaxParts + 1];   // peer mode: [owner-accumulated slice, rank 0's delta, rank 1's, ...]
     int n;
 };
 
@@ -101,10 +101,13 @@ struct PeerSync {
     int waited;                      // a k_peer_wait* launch ahead of this one on the stream already
                                      // observed the flags: the CTAs do not poll them again
 };
+// `accum` (may be null): the owner's accumulated slice; the merged record of every cell is stored back
+// into it (parts.part[0] then normally points at the same memory), so that the ranks only ever ship the
+// DELTA they accumulated since the previous finalize.
 cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t part_cell0, size_t cell0,
                                  size_t count, const OutTargets& out, size_t band_stride,
                                  const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
-                                 const PeerSync& ps, int sm_count);
+                                 const PeerSync& ps, uint32_t* accum, int sm_count);
 
 // Push phase of the peer-memory combine: every record of `state` that belongs to another rank's
 // row slice is stored (posted NVLink writes, no round trip) into that rank's combine buffer, slot
@@ -116,16 +119,19 @@ struct PushTargets {
     int rows_per;                    // rows per slice (ceil(height / world))
     size_t max_slice_cells;
 };
-cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint32_t* touched, int n_tiles,
+// `reset`: the pushed state is a delta buffer — every record (and touched flag) is put back to the
+// identity behind the copy, ready to take the ingests of the finalize after next.
+cudaError_t launch_push_slices(cudaStream_t s, uint32_t* state, uint32_t* touched, int n_tiles,
                                const GridParams& g, const PassLayout& L, const PushTargets& pt,
-                               const PeerSync& ps, bool push_touched, bool signal, int sm_count);
+                               const PeerSync& ps, bool push_touched, bool signal, bool reset, int sm_count);
 
 // store `epoch` into slot (phase, my rank) of every rank's flag array (system-scope release)
 cudaError_t launch_peer_signal(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch);
 // wait until every rank's slot of `phase` in MY flag array has reached `epoch`
 cudaError_t launch_peer_wait(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch);
 // wait (phase 0), then OR the touched-tile flags of all ranks into `merged`
+// (`cumulative`: OR into `merged` instead of overwriting it — the ranks pushed touched-flag deltas)
 cudaError_t launch_peer_wait_merge_touched(cudaStream_t s, const PeerFlags& pf, uint32_t epoch,
-                                           const PeerTouched& pt, uint32_t* merged, int n_tiles);
+                                           const PeerTouched& pt, uint32_t* merged, int n_tiles, bool cumulative);
 
 }  // namespace pcrb

@@ -54,6 +54,18 @@ __device__ __forceinline__ void load_record(const uint32_t* __restrict__ base, s
     }
 }
 
+template <int W>
+__device__ __forceinline__ void store_record(uint32_t* __restrict__ base, size_t cell, const uint32_t (&r)[8])
+{
+    if constexpr (W == 1) base[cell] = r[0];
+    if constexpr (W == 2) reinterpret_cast<uint2*>(base)[cell] = make_uint2(r[0], r[1]);
+    if constexpr (W == 4) reinterpret_cast<uint4*>(base)[cell] = make_uint4(r[0], r[1], r[2], r[3]);
+    if constexpr (W == 8) {
+        reinterpret_cast<uint4*>(base)[2 * cell]     = make_uint4(r[0], r[1], r[2], r[3]);
+        reinterpret_cast<uint4*>(base)[2 * cell + 1] = make_uint4(r[4], r[5], r[6], r[7]);
+    }
+}
+
 // One thread per cell of [cell0, cell0+count).  parts.part[k] points at the
 // record of cell `part_cell0` of rank k's partial state.
 // Merged record of one cell -> all bands of the pass.  The record words are parked in shared memory
@@ -63,7 +75,7 @@ template <int W>
 __device__ __forceinline__ void finalize_cell(const StateParts& parts, size_t part_cell0, size_t cell,
                                               const OutTargets& outs, size_t band_stride,
                                               const PassLayout& L, const FinalizeProgram& fp, bool live,
-                                              uint32_t (*s_words)[kThreads])
+                                              uint32_t (*s_words)[kThreads], uint32_t* accum = nullptr)
 {
     uint32_t r[8];
     load_record<W>(parts.part[0], cell - part_cell0, r);
@@ -80,6 +92,7 @@ __device__ __forceinline__ void finalize_cell(const StateParts& parts, size_t pa
                 r[j] = static_cast<uint32_t>(min(static_cast<int32_t>(r[j]), static_cast<int32_t>(q[j])));
         }
     }
+    if (accum) store_record<W>(accum, cell - part_cell0, r);      // the owner keeps the running merge
 #pragma unroll
     for (int j = 0; j < W; ++j) s_words[j][threadIdx.x] = r[j];   // own column only: no sync needed
 
@@ -238,9 +251,10 @@ __device__ __forceinline__ void wait_flag(const uint32_t* slot, uint32_t epoch)
 // (NVLink stores for foreign slices, a local copy for this rank's own slice).
 template <int W>
 __global__ void __launch_bounds__(kThreads)
-k_push_slices(const uint32_t* __restrict__ state, const uint32_t* __restrict__ touched, int n_tiles,
+k_push_slices(uint32_t* __restrict__ state, uint32_t* __restrict__ touched, int n_tiles,
               const __grid_constant__ GridParams g, const __grid_constant__ PushTargets pt,
-              const __grid_constant__ PeerSync ps, int push_touched, int signal)
+              const __grid_constant__ PeerSync ps, int push_touched, int signal, int reset,
+              const __grid_constant__ RecordIdentity id)
 {
     const PeerFlags& pf = ps.pf;
     // The peers' combine buffers may still be being read by their previous finalize: wait for
@@ -262,7 +276,7 @@ k_push_slices(const uint32_t* __restrict__ state, const uint32_t* __restrict__ t
         const unsigned owner = cell / per_owner;
         const unsigned local = cell - owner * per_owner;
         uint32_t* dst = pt.combined[owner] + (static_cast<size_t>(pf.rank) * pt.max_slice_cells + local) * W;
-        const uint32_t* src = state + static_cast<size_t>(cell) * W;
+        uint32_t* src = state + static_cast<size_t>(cell) * W;
         if constexpr (W == 1) dst[0] = src[0];
         if constexpr (W == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
         if constexpr (W == 4) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
@@ -270,11 +284,13 @@ k_push_slices(const uint32_t* __restrict__ state, const uint32_t* __restrict__ t
             reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
             reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
         }
+        if (reset) store_record<W>(state, cell, id.w);   // delta buffer: back to the identity behind the copy
     }
     if (push_touched && blockIdx.x == 0) {
         for (int t = threadIdx.x; t < n_tiles; t += kThreads) {
             const uint32_t v = touched[t];
             for (int k = 0; k < pf.n; ++k) pt.touched_stage[k][static_cast<size_t>(pf.rank) * n_tiles + t] = v;
+            if (reset) touched[t] = 0;
         }
     }
     if (signal) {
@@ -298,7 +314,8 @@ __global__ void __launch_bounds__(kThreads)
 k_finalize_peer(const __grid_constant__ StateParts parts, size_t part_cell0, size_t cell0, size_t count,
                 const __grid_constant__ OutTargets outs, size_t band_stride,
                 const __grid_constant__ GridParams g, const __grid_constant__ PassLayout L,
-                const __grid_constant__ FinalizeProgram fp, const __grid_constant__ PeerSync ps)
+                const __grid_constant__ FinalizeProgram fp, const __grid_constant__ PeerSync ps,
+                uint32_t* __restrict__ accum)
 {
     __shared__ uint32_t s_words[W][kThreads];
     const PeerFlags& pf = ps.pf;
@@ -316,7 +333,7 @@ k_finalize_peer(const __grid_constant__ StateParts parts, size_t part_cell0, siz
         const int t = (g.tiles_x * g.tiles_y == 1) ? 0 : tile_of(g, static_cast<int>(col), static_cast<int>(row));
         uint32_t live = 0;
         for (int k = 0; k < ps.pt.n; ++k) live |= __ldcg(ps.pt.touched[k] + t);
-        finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live != 0, s_words);
+        finalize_cell<W>(parts, part_cell0, cell, outs, band_stride, L, fp, live != 0, s_words, accum);
     }
 
     if (ps.signal_end) {
@@ -352,12 +369,12 @@ __global__ void k_peer_wait(const __grid_constant__ PeerFlags pf, int phase, uin
 
 __global__ void k_peer_wait_merge_touched(const __grid_constant__ PeerFlags pf, uint32_t epoch,
                                           const __grid_constant__ PeerTouched pt,
-                                          uint32_t* __restrict__ merged, int n_tiles)
+                                          uint32_t* __restrict__ merged, int n_tiles, int cumulative)
 {
     if (threadIdx.x < pf.n) wait_flag(pf.flags[pf.rank] + threadIdx.x, epoch);
     __syncthreads();
     for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
-        uint32_t v = 0;
+        uint32_t v = cumulative ? merged[t] : 0u;
         for (int k = 0; k < pt.n; ++k) v |= __ldcg(pt.touched[k] + t);
         merged[t] = v;
     }
@@ -365,15 +382,21 @@ __global__ void k_peer_wait_merge_touched(const __grid_constant__ PeerFlags pf, 
 
 }  // namespace
 
+static RecordIdentity identity_of(const PassLayout& L)
+{
+    RecordIdentity id{};
+    for (int j = 0; j < 8; ++j) id.w[j] = 0;
+    for (int j = 0; j < L.n_max; ++j) id.w[L.n_add + j] = static_cast<uint32_t>(f32_ordered(-FLT_MAX));
+    for (int j = 0; j < L.n_min; ++j) id.w[L.n_add + L.n_max + j] = static_cast<uint32_t>(f32_ordered(FLT_MAX));
+    return id;
+}
+
 cudaError_t launch_init_state(cudaStream_t s, uint32_t* state, size_t cells, const PassLayout& L)
 {
     if (cells == 0) return cudaSuccess;
     if (L.n_max == 0 && L.n_min == 0)
         return cudaMemsetAsync(state, 0, cells * L.width * sizeof(uint32_t), s);
-    RecordIdentity id{};
-    for (int j = 0; j < 8; ++j) id.w[j] = 0;
-    for (int j = 0; j < L.n_max; ++j) id.w[L.n_add + j] = static_cast<uint32_t>(f32_ordered(-FLT_MAX));
-    for (int j = 0; j < L.n_min; ++j) id.w[L.n_add + L.n_max + j] = static_cast<uint32_t>(f32_ordered(FLT_MAX));
+    const RecordIdentity id = identity_of(L);
     size_t blocks = (cells + kThreads - 1) / kThreads;
     if (blocks > 148 * 16) blocks = 148 * 16;
     const unsigned grid = static_cast<unsigned>(blocks);
@@ -429,18 +452,19 @@ cudaError_t launch_filter_mask(cudaStream_t s, const FilterProgram& fp, size_t n
     return cudaGetLastError();
 }
 
-cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint32_t* touched, int n_tiles,
+cudaError_t launch_push_slices(cudaStream_t s, uint32_t* state, uint32_t* touched, int n_tiles,
                                const GridParams& g, const PassLayout& L, const PushTargets& pt, const PeerSync& ps,
-                               bool push_touched, bool signal, int sm_count)
+                               bool push_touched, bool signal, bool reset, int sm_count)
 {
+    const RecordIdentity id = identity_of(L);
     const size_t cells = static_cast<size_t>(g.width) * g.height;
     const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((cells + kThreads - 1) / kThreads,
                                                                                      static_cast<size_t>(sm_count) * 8)));
     switch (L.width) {
-    case 1: k_push_slices<1><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
-    case 2: k_push_slices<2><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
-    case 4: k_push_slices<4><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
-    case 8: k_push_slices<8><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal); break;
+    case 1: k_push_slices<1><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal, reset, id); break;
+    case 2: k_push_slices<2><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal, reset, id); break;
+    case 4: k_push_slices<4><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal, reset, id); break;
+    case 8: k_push_slices<8><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal, reset, id); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -449,16 +473,16 @@ cudaError_t launch_push_slices(cudaStream_t s, const uint32_t* state, const uint
 cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t part_cell0, size_t cell0,
                                  size_t count, const OutTargets& out, size_t band_stride,
                                  const GridParams& g, const PassLayout& L, const FinalizeProgram& fp,
-                                 const PeerSync& ps, int sm_count)
+                                 const PeerSync& ps, uint32_t* accum, int sm_count)
 {
     // count may be 0 (a rank that owns no rows): the handshake still has to happen
     const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((count + kThreads - 1) / kThreads,
                                                                                      static_cast<size_t>(sm_count) * 8)));
     switch (L.width) {
-    case 1: k_finalize_peer<1><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
-    case 2: k_finalize_peer<2><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
-    case 4: k_finalize_peer<4><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
-    case 8: k_finalize_peer<8><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps); break;
+    case 1: k_finalize_peer<1><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps, accum); break;
+    case 2: k_finalize_peer<2><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps, accum); break;
+    case 4: k_finalize_peer<4><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps, accum); break;
+    case 8: k_finalize_peer<8><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps, accum); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -477,9 +501,9 @@ cudaError_t launch_peer_wait(cudaStream_t s, const PeerFlags& pf, int phase, uin
 }
 
 cudaError_t launch_peer_wait_merge_touched(cudaStream_t s, const PeerFlags& pf, uint32_t epoch,
-                                           const PeerTouched& pt, uint32_t* merged, int n_tiles)
+                                           const PeerTouched& pt, uint32_t* merged, int n_tiles, bool cumulative)
 {
-    k_peer_wait_merge_touched<<<1, 256, 0, s>>>(pf, epoch, pt, merged, n_tiles);
+    k_peer_wait_merge_touched<<<1, 256, 0, s>>>(pf, epoch, pt, merged, n_tiles, cumulative);
     return cudaGetLastError();
 }
 

@@ -773,7 +773,7 @@ class Pipeline:
         desc.warp_aggregate = int(getattr(cfg, "warp_aggregate", 0))
         desc.gaussian_kernel = int(getattr(cfg, "gaussian_kernel", 0))
         desc.comm_mode = int(getattr(cfg, "comm_mode", 0))
-        desc.comm_root_only = int(bool(getattr(cfg, "comm_root_only", False)))
+        desc.comm_root_only = int(getattr(cfg, "comm_root_only", 0))
         desc.async_ingest = int(bool(getattr(cfg, "async_ingest", False)))
         desc.comm_band_copy = int(getattr(cfg, "comm_band_copy", 0))
         preds = list(cfg.filter.predicates)
@@ -853,6 +853,22 @@ class Pipeline:
             views[i].dtype = int(desc.dtype)
         check(lib.pcr_pipeline_ingest(self._h, PointCloud._ptr(cloud._x), PointCloud._ptr(cloud._y),
                                       cloud.count(), views, len(names), int(cloud.location())))
+
+    def ingest_arrays(self, x_ptr, y_ptr, count, channels, location=MemoryLocation.Device):
+        """New: ingest borrowed raw buffers (addresses as ints) without a PointCloud object — e.g. arrays a
+        caller already holds in HBM.  channels = {name: address of `count` float32 values}.  Device buffers
+        must be complete (their producer stream synchronized) before the call."""
+        names = list(channels)
+        views = (_lib.ChannelView * max(len(names), 1))()
+        keep = []
+        for i, name in enumerate(names):
+            nb = _b(name)
+            keep.append(nb)
+            views[i].name = nb
+            views[i].data = int(channels[name])
+            views[i].dtype = int(DataType.Float32)
+        check(lib.pcr_pipeline_ingest(self._h, C.c_void_p(int(x_ptr)), C.c_void_p(int(y_ptr)), int(count), views,
+                                      len(names), int(location)))
 
     def _wrap_result(self):
         bands, arrays = [], []
@@ -958,6 +974,13 @@ class Pipeline:
 
     def comm_barrier(self):
         check(lib.pcr_pipeline_comm_barrier(self._h))
+
+
+def diag_red_ceiling(points=5_000_000, cells=1_000_000, with_loads=False, reps=20, device=0) -> float:
+    """Median microseconds the GPU needs for the Point kernel's reductions alone (measurement aid)."""
+    us = C.c_double(0.0)
+    check(lib.pcr_diag_red_ceiling(int(device), int(points), int(cells), int(bool(with_loads)), int(reps), C.byref(us)))
+    return us.value
 
 
 def comm_unique_id() -> bytes:
