@@ -110,7 +110,10 @@ typedef struct pcr_pipeline_desc {
     uint64_t                  ring_slot_points;     /* points per ring chunk, 0 = default (256 Ki staged
                                                        from pageable memory, 2 Mi direct from pinned) */
     int32_t                   staging_threads;      /* host copy threads, 0 = default */
-    int32_t                   point_kernel;         /* 0 = auto, 1 = direct LDG, 2 = TMA-staged persistent */
+    int32_t                   point_kernel;         /* 0 = auto (direct; tile-binned when the records exceed 256 MB),
+                                                       1 = direct LDG, 2 = TMA-staged persistent, 3 = tile-binned:
+                                                       entries {cell, value} are appended to per-bin page chains at
+                                                       ingest and folded bin by bin at finalize */
     int32_t                   warp_aggregate;       /* 0 = auto (adaptive run aggregation), 2 = off */
     int32_t                   gaussian_kernel;      /* 0 = auto, 1 = scatter (warp per point, REDs),
                                                        2 = gather (tile-binned, atomic-free, deterministic) */
@@ -128,6 +131,14 @@ typedef struct pcr_pipeline_desc {
     int32_t                   comm_band_copy;       /* N>1 peer mode, how a rank's finalized band slice reaches
                                                        the other ranks: 0/1 = stores from the merge kernel
                                                        (default), 2 = one copy-engine transfer per band and peer */
+    int32_t                   bin_cells_log2;       /* tile binning: a bin = 2^k consecutive cells; 0 = auto
+                                                       (the records of one bin <= 64 MB, at most 1024 bins) */
+    uint64_t                  bin_pool_points;      /* tile binning: entries the pool holds before it is folded
+                                                       early; 0 = auto (a quarter of the free HBM, <= 2^30) */
+    int32_t                   comm_layout;          /* N>1: 0 = auto, 1 = replicated partial grids merged at finalize,
+                                                       2 = tile-partitioned grid: every rank owns a contiguous range
+                                                       of bins, points are exchanged (all-to-all over NVLink peer
+                                                       memory, fused into the binning kernel), no reduce at finalize */
 } pcr_pipeline_desc;
 
 /* One named channel of a point cloud (pcr::PointCloud, include/pcr/core/point_cloud.h:29-103). */

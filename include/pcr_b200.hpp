@@ -498,9 +498,12 @@ struct PipelineConfig {
     int      staging_threads = 0;
     int      point_kernel = 0, warp_aggregate = 0, gaussian_kernel = 0;
     int      comm_mode = 0;
-    bool     comm_root_only = false;
+    int      comm_root_only = 0;        // 0 = bands complete on every rank, 1 = on rank 0 only, 2 = distributed
     bool     async_ingest = false;
     int      comm_band_copy = 0;
+    int      bin_cells_log2 = 0;        // tile binning (point_kernel = 3, or auto on large grids)
+    uint64_t bin_pool_points = 0;
+    int      comm_layout = 0;           // N>1: 0 auto, 1 replicated partial grids, 2 tile-partitioned grid
 };
 
 struct ProgressInfo {
@@ -561,11 +564,14 @@ public:
         d.warp_aggregate = c.warp_aggregate;
         d.gaussian_kernel = c.gaussian_kernel;
         d.comm_mode = c.comm_mode;
-        d.comm_root_only = c.comm_root_only ? 1 : 0;
+        d.comm_root_only = c.comm_root_only;
         d.filter = preds.empty() ? nullptr : preds.data();
         d.num_predicates = static_cast<int32_t>(preds.size());
         d.async_ingest = c.async_ingest ? 1 : 0;
         d.comm_band_copy = c.comm_band_copy;
+        d.bin_cells_log2 = c.bin_cells_log2;
+        d.bin_pool_points = c.bin_pool_points;
+        d.comm_layout = c.comm_layout;
         if (pcr_pipeline_create(&d, &p->h_) != PCR_OK || !p->h_) {
             const char* m = pcr_last_error();
             std::fprintf(stderr, "Pipeline::create failed: %s\n", m ? m : "");

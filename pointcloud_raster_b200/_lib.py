@@ -54,7 +54,8 @@ class PipelineDesc(C.Structure):
                 ("point_kernel", C.c_int32), ("warp_aggregate", C.c_int32),
                 ("gaussian_kernel", C.c_int32), ("comm_mode", C.c_int32), ("comm_root_only", C.c_int32),
                 ("filter", C.POINTER(FilterPredicate)), ("num_predicates", C.c_int32),
-                ("async_ingest", C.c_int32), ("comm_band_copy", C.c_int32)]
+                ("async_ingest", C.c_int32), ("comm_band_copy", C.c_int32),
+                ("bin_cells_log2", C.c_int32), ("bin_pool_points", C.c_uint64), ("comm_layout", C.c_int32)]
 
 
 class ChannelView(C.Structure):

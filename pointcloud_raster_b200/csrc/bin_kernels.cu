@@ -1,0 +1,397 @@
+// bin_kernels.cu — tile binning for the Point glyph on grids whose records do not fit L2, sm_100a.
+//
+// Reference counterpart: TileRouter::sort + extract_batches (src/engine/tile_router.cpp:138-366,
+// tile_router_kernels.cu:169-293) — the reference sorts every cloud by (tile, cell) so that a tile's
+// points are contiguous, then accumulates tile by tile.  Here the idea is kept and the sort is not:
+//
+//   * the grid's cell index space is cut into BINS of 2^shift consecutive cells whose records
+//     (<= 64 MB) stay resident in L2 while they are being updated;
+//   * k_bin_scatter routes each point ONCE (the CPU rule, common.cuh) and appends a compact entry
+//     {cell u32, value f32 ...} to the page chain of its bin.  A CTA stages 4096 points in shared
+//     memory, counting-sorts them by bin there (shared-memory integer atomics return the rank), and
+//     copies every bin's run out with coalesced stores into pages it owns exclusively — no global
+//     atomics per point, no inter-CTA waiting, one global atomic per 4096-entry page;
+//   * nothing is accumulated at ingest time.  Entries pile up (8 B per point and channel, pool sized
+//     from free HBM) until finalize — or until the pool is full — and only then k_bin_accumulate walks
+//     the pages bin by bin and issues the same reductions k_point_direct would have issued.  Deferring
+//     maximises the number of points per record sector per visit: every sector of a bin is fetched from
+//     HBM once and written back once per flush instead of once per point (profiles/r02_c5_*: the direct
+//     kernel moves 130 B of DRAM traffic per 20-B point on the 20000^2 grid).
+//
+// The same pages can live in ANOTHER rank's pool (peer memory): that is the tile-partitioned layout
+// with an all-to-all point exchange (engine_ext.cu, partition mode).
+#include "point_kernels_impl.cuh"
+#include "bin_kernels.cuh"
+
+namespace pcrb {
+
+namespace {
+
+using point_impl::RecordShape;
+using point_impl::pick;
+using point_impl::update_record;
+
+constexpr int kBinThreads = 256;
+constexpr int kBinPts = 16;                               // points per thread and chunk
+constexpr int kBinChunk = kBinThreads * kBinPts;          // 4096 = kBinPageEntries
+static_assert(kBinChunk == static_cast<int>(kBinPageEntries), "a chunk's run must fit two pages");
+constexpr uint32_t kNoPage = 0xffffffffu;
+
+// Exclusive scan of s_hist[0..nbins) into s_prefix, nbins <= kMaxBins = 4 * kBinThreads.
+__device__ __forceinline__ uint32_t block_scan_bins(const uint32_t* s_hist, uint32_t* s_prefix, int nbins,
+                                                    uint32_t* s_warp)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = tid * 4 + k;
+        v[k] = b < nbins ? s_hist[b] : 0u;
+        sum += v[k];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < kBinThreads / 32 ? s_warp[lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        if (lane < kBinThreads / 32) s_warp[lane] = w;     // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t run = inc - sum + (warp ? s_warp[warp - 1] : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = tid * 4 + k;
+        if (b < nbins) s_prefix[b] = run;
+        run += v[k];
+    }
+    return s_warp[kBinThreads / 32 - 1];                    // total
+}
+
+// One CTA = a persistent worker with its own page chain per bin (open_page / open_fill rows in global
+// memory survive from launch to launch, so a chain's only partly filled page is its last one).
+template <int NCH, bool EXACT>
+__global__ void __launch_bounds__(kBinThreads)
+k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
+              const __grid_constant__ ChannelPtrs ch, size_t n, const __grid_constant__ GridParams g,
+              const __grid_constant__ BinTargets bt, uint32_t* __restrict__ touched)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nbins = bt.nbins;
+    uint32_t* s_hist   = reinterpret_cast<uint32_t*>(smem_raw);          // [nbins]  points of this chunk per bin
+    uint32_t* s_prefix = s_hist + nbins;                                  // [nbins]  exclusive scan
+    uint32_t* s_seg_a  = s_prefix + nbins;                                // [nbins]  entry index of rank 0 (first page)
+    uint32_t* s_len_a  = s_seg_a + nbins;                                 // [nbins]  ranks served by the first page
+    uint32_t* s_seg_b  = s_len_a + nbins;                                 // [nbins]  entry index of rank len_a (second page)
+    uint32_t* s_pool   = s_seg_b + nbins;                                 // [nbins]  which pool (owner rank) the bin lives in
+    uint32_t* s_warp   = s_pool + nbins;                                  // [8]
+    uint32_t* st_pos   = s_warp + 8;                                      // [chunk]  destination entry index
+    uint32_t* st_cell  = st_pos + kBinChunk;                              // [chunk]
+    float*    st_val   = reinterpret_cast<float*>(st_cell + kBinChunk);   // [NCH][chunk]
+    uint8_t*  st_pool  = reinterpret_cast<uint8_t*>(st_val + static_cast<size_t>(NCH) * kBinChunk);   // [chunk]
+
+    const int tid = threadIdx.x;
+    uint32_t* my_open_page = bt.open_page + static_cast<size_t>(blockIdx.x) * nbins;
+    uint32_t* my_open_fill = bt.open_fill + static_cast<size_t>(blockIdx.x) * nbins;
+    const size_t nchunks = (n + kBinChunk - 1) / kBinChunk;
+    const bool multi_tile = g.tiles_x * g.tiles_y > 1;
+    bool any_valid = false;
+
+    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        for (int b = tid; b < nbins; b += kBinThreads) s_hist[b] = 0;
+        __syncthreads();
+
+        // ---- route; rank every point inside its bin with a shared-memory atomic ----
+        uint32_t cell[kBinPts], key[kBinPts];       // key = bin << 13 | rank  (rank < 4096), or ~0 = dropped
+        float val[kBinPts][NCH > 0 ? NCH : 1];
+        const size_t base = chunk * kBinChunk + tid;
+#pragma unroll
+        for (int q = 0; q < kBinPts; q += 4) {
+            double x[4], y[4];
+            bool live[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t i = base + static_cast<size_t>(q + u) * kBinThreads;
+                live[u] = i < n && (mask == nullptr || mask[i] != 0);
+                x[u] = live[u] ? ldg_stream_d(xs + i) : 0.0;
+                y[u] = live[u] ? ldg_stream_d(ys + i) : 0.0;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) val[q + u][c] = live[u] ? ldg_stream_f(ch.p[c] + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int col = 0, row = 0;
+                const bool ok = live[u] && route_cell<EXACT>(g, x[u], y[u], col, row);
+                const uint32_t c = static_cast<uint32_t>(row) * static_cast<uint32_t>(g.width) + static_cast<uint32_t>(col);
+                cell[q + u] = c;
+                key[q + u] = 0xffffffffu;
+                if (ok) {
+                    const uint32_t bin = c >> bt.shift;
+                    key[q + u] = (bin << 13) | atomicAdd(&s_hist[bin], 1u);
+                    any_valid = true;
+                    if (multi_tile) {                    // touched-tile rule, tile_manager.cpp:437-444
+                        const int t = tile_of(g, col, row);
+                        if (touched[t] == 0) touched[t] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- where does each bin's run go?  (page chain of this CTA; at most two pages per run) ----
+        const uint32_t total = block_scan_bins(s_hist, s_prefix, nbins, s_warp);
+        for (int b = tid; b < nbins; b += kBinThreads) {
+            const uint32_t cnt = s_hist[b];
+            if (cnt == 0) continue;
+            const int owner = bt.bin_owner_shift >= 0 ? static_cast<int>(static_cast<uint32_t>(b) / bt.bins_per_owner) : 0;
+            const BinPool& pool = bt.pool[owner];
+            uint32_t page = my_open_page[b], fill = my_open_fill[b];
+            auto alloc = [&]() -> uint32_t {
+                uint32_t pg = atomicAdd(pool.next_page, 1u);            // (a remote atomic when the pool is a peer's)
+                if (pg >= pool.pool_pages) { *pool.overflow = 1u; pg = pool.pool_pages - 1; }
+                pool.page_bin[pg] = static_cast<uint32_t>(b);
+                return pg;
+            };
+            if (page == kNoPage || fill == kBinPageEntries) { page = alloc(); fill = 0; }
+            const uint32_t len_a = min(cnt, kBinPageEntries - fill);
+            s_seg_a[b] = page * kBinPageEntries + fill;
+            s_len_a[b] = len_a;
+            s_pool[b] = static_cast<uint32_t>(owner);
+            pool.page_fill[page] = fill + len_a;
+            fill += len_a;
+            if (cnt > len_a) {
+                page = alloc();
+                fill = cnt - len_a;
+                s_seg_b[b] = page * kBinPageEntries;
+                pool.page_fill[page] = fill;
+            }
+            my_open_page[b] = page;
+            my_open_fill[b] = fill;
+        }
+        __syncthreads();
+
+        // ---- counting sort into the staging arrays ----
+#pragma unroll
+        for (int k = 0; k < kBinPts; ++k) {
+            if (key[k] == 0xffffffffu) continue;
+            const uint32_t bin = key[k] >> 13, rank = key[k] & 8191u;
+            const uint32_t at = s_prefix[bin] + rank;
+            st_pos[at] = rank < s_len_a[bin] ? s_seg_a[bin] + rank : s_seg_b[bin] + (rank - s_len_a[bin]);
+            st_cell[at] = cell[k];
+            st_pool[at] = static_cast<uint8_t>(s_pool[bin]);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) st_val[c * kBinChunk + at] = val[k][c];
+        }
+        __syncthreads();
+
+        // ---- copy out: consecutive threads = consecutive entries of one run = consecutive addresses ----
+        for (uint32_t t = tid; t < total; t += kBinThreads) {
+            const BinPool& pool = bt.pool[st_pool[t]];
+            const uint32_t at = st_pos[t];
+            pool.ent_cell[at] = st_cell[t];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) pool.ent_val[c][at] = st_val[c * kBinChunk + t];
+        }
+        __syncthreads();
+    }
+    if (!multi_tile) {
+        if (__any_sync(0xffffffffu, any_valid) && (tid & 31) == 0 && touched[0] == 0) touched[0] = 1;
+    }
+}
+
+// ---- flush: order the pages by bin, then fold them ----
+__global__ void k_bin_page_count(const __grid_constant__ BinPool pool, uint32_t* __restrict__ bin_pages)
+{
+    const uint32_t np = min(*pool.next_page, pool.pool_pages);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
+        atomicAdd(&bin_pages[pool.page_bin[p]], 1u);
+}
+
+// single CTA: exclusive scan of bin_pages[0..nbins) -> bin_first; bin_pages becomes the running cursor
+__global__ void k_bin_page_scan(uint32_t* __restrict__ bin_pages, uint32_t* __restrict__ bin_first, int nbins)
+{
+    __shared__ uint32_t s[kMaxBins];
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) s[b] = bin_pages[b];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < nbins; ++b) { const uint32_t c = s[b]; s[b] = run; run += c; }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) { bin_first[b] = s[b]; bin_pages[b] = 0; }
+}
+
+__global__ void k_bin_page_order(const __grid_constant__ BinPool pool, const uint32_t* __restrict__ bin_first,
+                                 uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ order)
+{
+    const uint32_t np = min(*pool.next_page, pool.pool_pages);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        const uint32_t b = pool.page_bin[p];
+        order[bin_first[b] + atomicAdd(&bin_cursor[b], 1u)] = p;
+    }
+}
+
+// CTA per page, pages in bin order: at any time the resident CTAs work on neighbouring bins, whose
+// records stay in L2.  Same reductions per entry as k_point_direct (update_record).
+template <int NADD, int NMAX, int NMIN, int NCH>
+__global__ void __launch_bounds__(kBinThreads)
+k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restrict__ order,
+                 uint32_t* __restrict__ state, size_t cell_base, const __grid_constant__ PassLayout L)
+{
+    const uint32_t np = min(*pool.next_page, pool.pool_pages);
+    for (uint32_t i = blockIdx.x; i < np; i += gridDim.x) {
+        const uint32_t page = order[i];
+        const uint32_t cnt = min(pool.page_fill[page], kBinPageEntries);
+        const uint32_t e0 = page * kBinPageEntries;
+#pragma unroll 4
+        for (uint32_t t = threadIdx.x; t < cnt; t += kBinThreads) {
+            const uint32_t cell = __ldcs(pool.ent_cell + e0 + t);
+            float v[kMaxChan] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) v[c] = __ldcs(pool.ent_val[c] + e0 + t);
+            float add[kMaxAdd], mx[kMaxExt], mn[kMaxExt];
+#pragma unroll
+            for (int j = 0; j < kMaxAdd; ++j) add[j] = (j < NADD) ? (L.add_src[j] < 0 ? 1.0f : pick(v, L.add_src[j])) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < kMaxExt; ++j) mx[j] = (j < NMAX) ? pick(v, L.max_src[j]) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < kMaxExt; ++j) mn[j] = (j < NMIN) ? pick(v, L.min_src[j]) : 0.0f;
+            update_record<NADD, NMAX, NMIN>(state, static_cast<size_t>(cell) - cell_base, add, mx, mn);
+        }
+    }
+}
+
+// everything back to "empty pool"; the CTA chains forget their open pages
+__global__ void k_bin_reset(const __grid_constant__ BinPool pool, uint32_t* __restrict__ open_page, size_t n_open)
+{
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i == 0) *pool.next_page = 0;
+    for (size_t k = i; k < n_open; k += static_cast<size_t>(gridDim.x) * blockDim.x) open_page[k] = kNoPage;
+}
+
+template <int NADD, int NMAX, int NMIN>
+cudaError_t acc_nch(cudaStream_t s, unsigned grid, const BinPool& pool, const uint32_t* order, uint32_t* state,
+                    size_t cell_base, const PassLayout& L)
+{
+    switch (L.n_chan) {
+    case 0: k_bin_accumulate<NADD, NMAX, NMIN, 0><<<grid, kBinThreads, 0, s>>>(pool, order, state, cell_base, L); break;
+    case 1: k_bin_accumulate<NADD, NMAX, NMIN, 1><<<grid, kBinThreads, 0, s>>>(pool, order, state, cell_base, L); break;
+    case 2: k_bin_accumulate<NADD, NMAX, NMIN, 2><<<grid, kBinThreads, 0, s>>>(pool, order, state, cell_base, L); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int NADD, int NMAX>
+cudaError_t acc_min(cudaStream_t s, unsigned grid, const BinPool& pool, const uint32_t* order, uint32_t* state,
+                    size_t cell_base, const PassLayout& L)
+{
+    switch (L.n_min) {
+    case 0: if constexpr (NADD + NMAX > 0) return acc_nch<NADD, NMAX, 0>(s, grid, pool, order, state, cell_base, L);
+            else return cudaErrorInvalidValue;
+    case 1: return acc_nch<NADD, NMAX, 1>(s, grid, pool, order, state, cell_base, L);
+    case 2: return acc_nch<NADD, NMAX, 2>(s, grid, pool, order, state, cell_base, L);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int NADD>
+cudaError_t acc_max(cudaStream_t s, unsigned grid, const BinPool& pool, const uint32_t* order, uint32_t* state,
+                    size_t cell_base, const PassLayout& L)
+{
+    switch (L.n_max) {
+    case 0: return acc_min<NADD, 0>(s, grid, pool, order, state, cell_base, L);
+    case 1: return acc_min<NADD, 1>(s, grid, pool, order, state, cell_base, L);
+    case 2: return acc_min<NADD, 2>(s, grid, pool, order, state, cell_base, L);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool bin_supported(const PassLayout& L) { return L.n_chan <= kBinMaxChan; }
+
+size_t bin_scatter_smem(int nbins, int n_chan)
+{
+    return static_cast<size_t>(6 * nbins + 8) * 4 + static_cast<size_t>(kBinChunk) * (8 + 4 * n_chan + 1);
+}
+
+unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan)
+{
+    // CTAs per SM by shared memory (227 KB usable), at most 2 (<= 106 registers x 256 threads)
+    const size_t per = bin_scatter_smem(nbins, n_chan);
+    const unsigned by_smem = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / per)));
+    return static_cast<unsigned>(sm_count) * by_smem;
+}
+
+cudaError_t launch_bin_scatter(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
+                               const ChannelPtrs& ch, size_t n, const GridParams& g, const PassLayout& L,
+                               const BinTargets& bt, uint32_t* touched, unsigned grid)
+{
+    if (n == 0) return cudaSuccess;
+    const size_t smem = bin_scatter_smem(bt.nbins, L.n_chan);
+    const bool exact = g.exact_x && g.exact_y;
+#define PCR_BIN_LAUNCH(NCH, EX)                                                                             \
+    do {                                                                                                    \
+        auto kern = k_bin_scatter<NCH, EX>;                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                             static_cast<int>(smem));                                      \
+        if (e != cudaSuccess) return e;                                                                     \
+        kern<<<grid, kBinThreads, smem, s>>>(mask, x, y, ch, n, g, bt, touched);                            \
+    } while (0)
+    switch (L.n_chan * 2 + (exact ? 1 : 0)) {
+    case 0: PCR_BIN_LAUNCH(0, false); break;
+    case 1: PCR_BIN_LAUNCH(0, true); break;
+    case 2: PCR_BIN_LAUNCH(1, false); break;
+    case 3: PCR_BIN_LAUNCH(1, true); break;
+    case 4: PCR_BIN_LAUNCH(2, false); break;
+    case 5: PCR_BIN_LAUNCH(2, true); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef PCR_BIN_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bin_flush(cudaStream_t s, const BinPool& pool, int nbins, uint32_t* bin_pages, uint32_t* bin_first,
+                             uint32_t* order, uint32_t* state, size_t cell_base, const PassLayout& L,
+                             uint32_t* open_page, size_t n_open, int sm_count)
+{
+    const unsigned g1 = static_cast<unsigned>(sm_count) * 4;
+    k_bin_page_count<<<g1, 256, 0, s>>>(pool, bin_pages);
+    k_bin_page_scan<<<1, 256, 0, s>>>(bin_pages, bin_first, nbins);
+    k_bin_page_order<<<g1, 256, 0, s>>>(pool, bin_first, bin_pages, order);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const unsigned ga = static_cast<unsigned>(sm_count) * 8;
+    switch (L.n_add) {
+    case 0: e = acc_max<0>(s, ga, pool, order, state, cell_base, L); break;
+    case 1: e = acc_max<1>(s, ga, pool, order, state, cell_base, L); break;
+    case 2: e = acc_max<2>(s, ga, pool, order, state, cell_base, L); break;
+    case 3: e = acc_max<3>(s, ga, pool, order, state, cell_base, L); break;
+    case 4: e = acc_max<4>(s, ga, pool, order, state, cell_base, L); break;
+    default: e = cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    // bin_pages was the scatter cursor of k_bin_page_order: zero it for the next flush
+    e = cudaMemsetAsync(bin_pages, 0, static_cast<size_t>(nbins) * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    k_bin_reset<<<g1, 256, 0, s>>>(pool, open_page, n_open);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bin_reset(cudaStream_t s, const BinPool& pool, uint32_t* open_page, size_t n_open, int sm_count)
+{
+    k_bin_reset<<<static_cast<unsigned>(sm_count) * 4, 256, 0, s>>>(pool, open_page, n_open);
+    return cudaGetLastError();
+}
+
+}  // namespace pcrb

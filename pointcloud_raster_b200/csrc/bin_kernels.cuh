@@ -1,0 +1,48 @@
+// bin_kernels.cuh — interface of the tile-binning path (bin_kernels.cu).
+#pragma once
+
+#include "kernels.cuh"
+
+namespace pcrb {
+
+constexpr uint32_t kBinPageEntries = 4096;   // entries per page (= points per scatter chunk)
+constexpr int kMaxBins = 1024;
+constexpr int kBinMaxChan = 2;               // value channels an entry can carry
+
+// One rank's entry pool (device pointers; another rank's pool is the same struct over peer memory).
+struct BinPool {
+    uint32_t* ent_cell;                      // [pool_pages * kBinPageEntries] global cell index
+    float*    ent_val[kBinMaxChan];          // [...] channel values, SoA
+    uint32_t* page_bin;                      // [pool_pages] bin a page belongs to
+    uint32_t* page_fill;                     // [pool_pages] entries written to a page so far
+    uint32_t* next_page;                     // pages handed out so far
+    uint32_t* overflow;                      // set to 1 if the pool ran out (entries were dropped)
+    uint32_t  pool_pages;
+};
+
+// Where the scatter kernel sends a bin's entries.
+struct BinTargets {
+    BinPool pool[kMaxParts];                 // pool of the rank that owns the bin (pool[0] on one GPU)
+    int bin_owner_shift;                     // < 0: everything is pool[0]
+    uint32_t bins_per_owner;                 // owner = bin / bins_per_owner
+    int shift;                               // bin = cell >> shift
+    int nbins;
+    uint32_t* open_page;                     // [scatter grid][nbins] page chains of this rank's scatter CTAs
+    uint32_t* open_fill;
+};
+
+bool bin_supported(const PassLayout& L);
+size_t bin_scatter_smem(int nbins, int n_chan);
+unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan);
+// route n points once and append {cell, values} to the page chain of each point's bin
+cudaError_t launch_bin_scatter(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
+                               const ChannelPtrs& ch, size_t n, const GridParams& g, const PassLayout& L,
+                               const BinTargets& bt, uint32_t* touched, unsigned grid);
+// fold every pending entry of `pool` into `state` (record of global cell c at state[(c - cell_base) * W]),
+// bin by bin, and empty the pool
+cudaError_t launch_bin_flush(cudaStream_t s, const BinPool& pool, int nbins, uint32_t* bin_pages, uint32_t* bin_first,
+                             uint32_t* order, uint32_t* state, size_t cell_base, const PassLayout& L,
+                             uint32_t* open_page, size_t n_open, int sm_count);
+cudaError_t launch_bin_reset(cudaStream_t s, const BinPool& pool, uint32_t* open_page, size_t n_open, int sm_count);
+
+}  // namespace pcrb

@@ -84,6 +84,7 @@ Status Engine::save_state(const std::string& dir)
         return Status::error(PCR_NOT_IMPLEMENTED,
                              "pipeline: save_state is not available on a multi-GPU pipeline (the accumulated state "
                              "is distributed over the ranks' row slices); checkpoint from a single-GPU pipeline");
+    ST_TRY(bin_flush_all());
     ST_TRY(synchronize());
     if (!make_dir(dir)) return Status::error(PCR_IO_ERROR, "failed to create state directory: " + dir);
     std::vector<uint32_t> touched(std::max(1, n_tiles_));
@@ -136,6 +137,7 @@ Status Engine::save_state(const std::string& dir)
 Status Engine::load_state(const std::string& dir)
 {
     CU_TRY(cudaSetDevice(device_));
+    ST_TRY(bin_flush_all());
     ST_TRY(synchronize());
     // N>1: the files are ONE contribution to the merged state; rank 0 takes them into its partial state
     // (merged into the owners' slices at the next finalize), the other ranks keep the identity — loading

@@ -336,6 +336,10 @@ Status Engine::init(const pcr_pipeline_desc& d)
     deterministic_ = d.deterministic != 0;
     async_device_ingest_ = d.async_ingest != 0;
     point_variant_ = d.point_kernel == 2 ? POINT_TMA : d.point_kernel == 1 ? POINT_DIRECT : POINT_DIRECT;
+    point_kernel_knob_ = d.point_kernel;
+    bin_cells_log2_ = d.bin_cells_log2;
+    bin_pool_points_ = d.bin_pool_points;
+    comm_layout_ = d.comm_layout;
     warp_aggregate_ = d.warp_aggregate != 2;
     gaussian_variant_ = d.gaussian_kernel;
     comm_mode_ = d.comm_mode;
@@ -482,6 +486,7 @@ Status Engine::alloc_state()
         CU_TRY(cudaMalloc(&d_survivors_, sizeof(unsigned long long)));
         CU_TRY(cudaMemset(d_survivors_, 0, sizeof(unsigned long long)));
     }
+    for (Pass& p : passes_) ST_TRY(bin_setup(p));      // last: the entry pools take their share of what is left
     return Status::success();
 }
 
@@ -510,6 +515,11 @@ Status Engine::reset()
     CU_TRY(cudaSetDevice(device_));
     ST_TRY(synchronize());
     ST_TRY(init_state());
+    for (Pass& p : passes_)
+        if (p.bin.on) {
+            CU_TRY(launch_bin_reset(compute_, p.bin.pool, p.bin.open_page, static_cast<size_t>(p.bin.grid) * p.bin.nbins, sm_count_));
+            p.bin.pending = 0;
+        }
     if (d_survivors_) CU_TRY(cudaMemsetAsync(d_survivors_, 0, sizeof(unsigned long long), compute_));
     collections_ = 0;
     points_ = 0;
@@ -545,7 +555,8 @@ Engine::~Engine()
     }
     peer_unmap();
     if (comm_) engine_comm_destroy(nccl_, comm_);
-    for (Pass& p : passes_) { cudaFree(p.d_delta[0]); cudaFree(p.d_delta[1]); cudaFree(p.d_owned); cudaFree(p.d_combined); }
+    for (Pass& p : passes_) { cudaFree(p.d_delta[0]); cudaFree(p.d_delta[1]); cudaFree(p.d_owned); cudaFree(p.d_combined); bin_free(p); }
+    if (h_overflow_) cudaFreeHost(h_overflow_);
     cudaFree(d_touched_buf_[0]);
     cudaFree(d_touched_buf_[1]);
     if (e_delta_) cudaEventDestroy(e_delta_);
@@ -843,8 +854,22 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
     const uint8_t* mask = nullptr;
     ST_TRY(build_mask(n, cp, &mask));
     if (deterministic_) ST_TRY(run_passes_deterministic(dx, dy, n, cp, mask));
+    // tile-binned Point passes only append entries now; their reductions run bin by bin at finalize
+    bool any_binned = false;
+    for (Pass& p : passes_) any_binned = any_binned || p.bin.on;
+    if (any_binned) {
+        prof_begin(PROF_SORT, compute_);
+        for (Pass& p : passes_) {
+            if (!p.bin.on) continue;
+            ChannelPtrs ch{};
+            for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])];
+            ST_TRY(bin_append(p, mask, dx, dy, ch, n));
+        }
+        prof_end(compute_);
+    }
     prof_begin(PROF_ACC, compute_);
     for (Pass& p : passes_) {
+        if (p.bin.on) continue;
         if (deterministic_ && p.glyph.type == PCR_GLYPH_POINT) continue;   // folded by the sort path above
         ChannelPtrs ch{};
         for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])];
@@ -1074,6 +1099,7 @@ Status Engine::ingest_host(const double* x, const double* y, size_t n,
 Status Engine::finalize(bool to_host)
 {
     CU_TRY(cudaSetDevice(device_));
+    ST_TRY(bin_flush_all());
     if (world_ > 1) ST_TRY(finalize_multi());
     else ST_TRY(finalize_single());
     if (to_host || !async_device_ingest_) {
@@ -1086,7 +1112,16 @@ Status Engine::finalize(bool to_host)
         CU_TRY(cudaMemcpyAsync(h_out_, d_out_, bytes, cudaMemcpyDeviceToHost, compute_));
         prof_d2h_ += bytes;
     }
-    if (to_host || !async_device_ingest_) CU_TRY(cudaStreamSynchronize(compute_));
+    const bool syncing = to_host || !async_device_ingest_;
+    int n_ovf = 0;
+    if (syncing && h_overflow_)
+        for (Pass& p : passes_)
+            if (p.bin.on && n_ovf < 16)
+                CU_TRY(cudaMemcpyAsync(h_overflow_ + n_ovf++, p.bin.pool.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, compute_));
+    if (syncing) CU_TRY(cudaStreamSynchronize(compute_));
+    for (int i = 0; i < n_ovf; ++i)
+        if (h_overflow_[i])
+            return Status::error(PCR_OUT_OF_MEMORY, "pipeline: the tile-binning entry pool overflowed (points were dropped)");
     finalized_ = true;
     return Status::success();
 }

@@ -23,6 +23,7 @@
 
 #include "../../include/pcr_b200.h"
 #include "kernels.cuh"
+#include "bin_kernels.cuh"
 
 namespace pcrb {
 
@@ -58,6 +59,20 @@ struct FilterPredHost {
     std::vector<float> set;
 };
 
+// Tile binning of a Point pass on a grid whose records do not fit L2 (bin_kernels.cu): entries are
+// appended to per-bin page chains at ingest time and folded into the records bin by bin at finalize
+// (or when the pool is full).
+struct BinState {
+    bool on = false;
+    int shift = 0, nbins = 0;
+    BinPool pool{};
+    uint32_t *bin_pages = nullptr, *bin_first = nullptr, *order = nullptr;
+    uint32_t *open_page = nullptr, *open_fill = nullptr;   // [grid][nbins] chains of this rank's scatter CTAs
+    unsigned grid = 0;
+    uint64_t pending = 0;           // points appended since the last flush (upper bound of entries)
+    uint64_t capacity = 0;          // points the pool takes whatever their distribution over the bins
+};
+
 // One fused pass: every reduction in it shares the glyph footprint.
 struct Pass {
     GlyphSpecHost glyph;
@@ -71,6 +86,7 @@ struct Pass {
     // that owns a row slice keeps the running merge of everybody's deltas in d_owned.
     uint32_t* d_delta[2] = {nullptr, nullptr};
     uint32_t* d_owned = nullptr;         // my row slice, accumulated over all finalizes so far
+    BinState bin;
 };
 
 // Worker pool for the pageable -> pinned staging copies of one host ingest.
@@ -177,6 +193,11 @@ private:
                          const std::vector<const float*>& chan_ptrs);
     Status ingest_host(const double* x, const double* y, size_t n,
                        const std::vector<const float*>& chan_ptrs, bool pinned);
+    Status bin_setup(Pass& p);            // decide + allocate the entry pool of a Point pass
+    Status bin_append(Pass& p, const uint8_t* mask, const double* dx, const double* dy, const ChannelPtrs& ch, size_t n);
+    Status bin_flush(Pass& p);            // fold the pending entries into the records (compute stream)
+    Status bin_flush_all();
+    void bin_free(Pass& p);
     Status finalize_single();
     Status finalize_multi();
     Status finalize_multi_nccl();
@@ -202,6 +223,10 @@ private:
     bool deterministic_ = false;
     bool async_device_ingest_ = false;
     int point_variant_ = POINT_DIRECT;
+    int point_kernel_knob_ = 0;       // pcr_pipeline_desc::point_kernel as given (3 = force the binned path)
+    int bin_cells_log2_ = 0;          // 0 = auto (records of one bin <= 64 MB)
+    uint64_t bin_pool_points_ = 0;    // 0 = auto (from free HBM)
+    uint32_t* h_overflow_ = nullptr;  // pinned read-back of the pools' overflow flags
     bool warp_aggregate_ = true;
     size_t cells_ = 0;
     int n_tiles_ = 0;
@@ -296,6 +321,7 @@ private:
     int rank_ = 0, world_ = 1;
     // peer-memory path: every rank's state / touched / bands / flags mapped into this process
     bool peer_ok_ = false;
+    int comm_layout_ = 0;             // 0 auto, 1 replicated partial grids, 2 tile-partitioned
     int comm_mode_ = 0;               // 0 auto (peer memory when every pair has P2P), 1 NCCL, 2 peer
     bool gather_root_only_ = false;
     bool bands_distributed_ = false;  // N>1: every rank keeps only its own row slice of the bands

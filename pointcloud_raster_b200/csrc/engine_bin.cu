@@ -1,0 +1,142 @@
+// engine_bin.cu — host side of the tile-binning path (kernels: bin_kernels.cu).
+//
+// When a Point pass runs on a grid whose records are far larger than L2 (BASELINE config 5: 20000^2
+// cells, 6.4 GB of records), k_point_direct pays a DRAM read-modify-write of a 32-byte sector for
+// every point (profiles/r02_c5_point_direct_ncu_full.json).  The binned path replaces
+// "route + reduce now" by "route + append now, reduce bin by bin later": the role of the reference's
+// TileRouter::sort / extract_batches (src/engine/tile_router.cpp:138-366) without a sort.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace pcrb {
+
+#define CU_TRY(expr)                                                                     \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return Status::error(PCR_CUDA_ERROR, std::string("CUDA error: ") +           \
+                                 cudaGetErrorString(_e) + " (" #expr ")");               \
+    } while (0)
+#define ST_TRY(expr) do { Status _s = (expr); if (!_s.ok()) return _s; } while (0)
+
+// Decide whether pass `p` is binned and allocate its pool.  Called from alloc_state().
+Status Engine::bin_setup(Pass& p)
+{
+    BinState& b = p.bin;
+    b.on = false;
+    if (p.glyph.type != PCR_GLYPH_POINT || deterministic_ || !bin_supported(p.layout)) return Status::success();
+    const size_t W = p.layout.width;
+    const size_t state_bytes = cells_ * W * 4;
+    const bool forced = point_kernel_knob_ == 3;
+    // auto: only where the records cannot live in L2 (126 MB) anyway
+    if (!forced && !(point_kernel_knob_ == 0 && state_bytes >= (size_t(256) << 20))) return Status::success();
+
+    // bin = 2^shift consecutive cells; auto: the records of a bin fill at most 64 MB, at most kMaxBins bins
+    int shift = bin_cells_log2_;
+    if (shift <= 0) {
+        shift = 4;
+        while ((size_t(2) << shift) * W * 4 <= (size_t(64) << 20)) ++shift;
+    }
+    shift = std::max(4, std::min(shift, 31));
+    while (((cells_ + (size_t(1) << shift) - 1) >> shift) > static_cast<size_t>(kMaxBins)) ++shift;
+    b.shift = shift;
+    b.nbins = static_cast<int>((cells_ + (size_t(1) << shift) - 1) >> shift);
+    b.grid = bin_scatter_grid(sm_count_, b.nbins, p.layout.n_chan);
+    const size_t chains = static_cast<size_t>(b.grid) * b.nbins;
+
+    // pool size: every chain ends in one partly filled page, all other pages are full, so T points need at
+    // most T / P + chains pages whatever their distribution
+    const size_t entry_bytes = 4 + 4 * static_cast<size_t>(p.layout.n_chan);
+    size_t want = bin_pool_points_;
+    if (want == 0) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        want = std::min<size_t>(size_t(1) << 30, free_b / 4 / entry_bytes);
+    }
+    want = std::max<size_t>(want, kBinPageEntries);
+    const size_t pages = want / kBinPageEntries + chains + 1;
+    if (pages >= (size_t(1) << 20) * 1024 / kBinPageEntries * 4)     // entry indices are 32-bit
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: bin_pool_points too large");
+    b.pool.pool_pages = static_cast<uint32_t>(pages);
+    b.capacity = (pages - chains - 1) * kBinPageEntries;
+    const size_t entries = pages * kBinPageEntries;
+    CU_TRY(cudaMalloc(&b.pool.ent_cell, entries * 4));
+    for (int c = 0; c < p.layout.n_chan; ++c) CU_TRY(cudaMalloc(&b.pool.ent_val[c], entries * 4));
+    CU_TRY(cudaMalloc(&b.pool.page_bin, pages * 4));
+    CU_TRY(cudaMalloc(&b.pool.page_fill, pages * 4));
+    CU_TRY(cudaMalloc(&b.pool.next_page, 2 * sizeof(uint32_t)));
+    b.pool.overflow = b.pool.next_page + 1;
+    CU_TRY(cudaMemsetAsync(b.pool.next_page, 0, 2 * sizeof(uint32_t), compute_));
+    CU_TRY(cudaMalloc(&b.bin_pages, static_cast<size_t>(b.nbins) * 4));
+    CU_TRY(cudaMalloc(&b.bin_first, static_cast<size_t>(b.nbins) * 4));
+    CU_TRY(cudaMemsetAsync(b.bin_pages, 0, static_cast<size_t>(b.nbins) * 4, compute_));
+    CU_TRY(cudaMalloc(&b.order, pages * 4));
+    CU_TRY(cudaMalloc(&b.open_page, chains * 4));
+    CU_TRY(cudaMalloc(&b.open_fill, chains * 4));
+    CU_TRY(cudaMemsetAsync(b.open_page, 0xFF, chains * 4, compute_));
+    CU_TRY(cudaMemsetAsync(b.open_fill, 0, chains * 4, compute_));
+    if (!h_overflow_) CU_TRY(cudaMallocHost(&h_overflow_, sizeof(uint32_t) * 16));
+    b.pending = 0;
+    b.on = true;
+    return Status::success();
+}
+
+void Engine::bin_free(Pass& p)
+{
+    BinState& b = p.bin;
+    cudaFree(b.pool.ent_cell);
+    for (float* v : b.pool.ent_val) cudaFree(v);
+    cudaFree(b.pool.page_bin); cudaFree(b.pool.page_fill); cudaFree(b.pool.next_page);
+    cudaFree(b.bin_pages); cudaFree(b.bin_first); cudaFree(b.order); cudaFree(b.open_page); cudaFree(b.open_fill);
+    b = BinState{};
+}
+
+// Append one device-resident chunk.  Folds the pool first when the chunk would not fit.
+Status Engine::bin_append(Pass& p, const uint8_t* mask, const double* dx, const double* dy, const ChannelPtrs& ch, size_t n)
+{
+    BinState& b = p.bin;
+    size_t done = 0;
+    while (done < n) {
+        if (b.pending >= b.capacity) ST_TRY(bin_flush(p));
+        const size_t cnt = std::min<size_t>(n - done, b.capacity - b.pending);
+        ChannelPtrs c2 = ch;
+        for (int c = 0; c < p.layout.n_chan; ++c) c2.p[c] = ch.p[c] + done;
+        BinTargets bt{};
+        bt.pool[0] = b.pool;
+        bt.bin_owner_shift = -1;
+        bt.bins_per_owner = static_cast<uint32_t>(b.nbins);
+        bt.shift = b.shift;
+        bt.nbins = b.nbins;
+        bt.open_page = b.open_page;
+        bt.open_fill = b.open_fill;
+        CU_TRY(launch_bin_scatter(compute_, mask ? mask + done : nullptr, dx + done, dy + done, c2, cnt, gp_, p.layout, bt,
+                                  d_touched_, b.grid));
+        ++launches_;
+        b.pending += cnt;
+        done += cnt;
+    }
+    return Status::success();
+}
+
+Status Engine::bin_flush(Pass& p)
+{
+    BinState& b = p.bin;
+    if (!b.on || b.pending == 0) return Status::success();
+    prof_begin(PROF_ACC, compute_);
+    CU_TRY(launch_bin_flush(compute_, b.pool, b.nbins, b.bin_pages, b.bin_first, b.order, p.d_state, 0, p.layout,
+                            b.open_page, static_cast<size_t>(b.grid) * b.nbins, sm_count_));
+    launches_ += 5;
+    prof_end(compute_);
+    b.pending = 0;
+    return Status::success();
+}
+
+Status Engine::bin_flush_all()
+{
+    for (Pass& p : passes_) ST_TRY(bin_flush(p));
+    return Status::success();
+}
+
+}  // namespace pcrb

@@ -698,6 +698,9 @@ class PipelineConfig:
         self.comm_root_only = False
         self.async_ingest = False
         self.comm_band_copy = 0
+        self.bin_cells_log2 = 0
+        self.bin_pool_points = 0
+        self.comm_layout = 0
 
 
 class ProgressInfo:
@@ -776,6 +779,9 @@ class Pipeline:
         desc.comm_root_only = int(getattr(cfg, "comm_root_only", 0))
         desc.async_ingest = int(bool(getattr(cfg, "async_ingest", False)))
         desc.comm_band_copy = int(getattr(cfg, "comm_band_copy", 0))
+        desc.bin_cells_log2 = int(getattr(cfg, "bin_cells_log2", 0))
+        desc.bin_pool_points = int(getattr(cfg, "bin_pool_points", 0))
+        desc.comm_layout = int(getattr(cfg, "comm_layout", 0))
         preds = list(cfg.filter.predicates)
         if preds:
             arr = (_lib.FilterPredicate * len(preds))()
