@@ -188,6 +188,9 @@ def build_pipeline(pcr, device, async_ingest, rank=0, world=1, unique_id=None, g
     cfg.ring_slot_points = int(os.environ.get("PCR_RING_SLOT", "0"))
     cfg.ring_depth = int(os.environ.get("PCR_RING_DEPTH", "0"))
     cfg.staging_threads = int(os.environ.get("PCR_STAGING_THREADS", "0"))
+    cfg.bin_cells_log2 = int(os.environ.get("PCR_BIN_LOG2", "0"))
+    cfg.bin_pool_points = int(float(os.environ.get("PCR_BIN_POOL", "0")))
+    cfg.comm_layout = int(os.environ.get("PCR_COMM_LAYOUT", "0"))
     # N>1: the finished raster is assembled on rank 0 (the rank that would write the GeoTIFF);
     # the other ranks keep only their own row slice.  PCR_COMM_ROOT_ONLY=0 gives every rank all bands.
     cfg.comm_root_only = int(os.environ.get("PCR_COMM_ROOT_ONLY", "1")) if root_only is None else root_only
@@ -420,6 +423,10 @@ def c5_chunk(torch, j, device):
     g = torch.Generator(device=device)
     g.manual_seed(42 + j)
     which = torch.randint(0, K, (C5_CHUNK,), generator=g, device=device)
+    if os.environ.get("PCR_C5_DIST") == "uniform":      # development aid: no hot cells
+        x = torch.rand(C5_CHUNK, generator=g, device=device, dtype=torch.float64) * C5_GRID
+        y = torch.rand(C5_CHUNK, generator=g, device=device, dtype=torch.float64) * C5_GRID
+        return x, y, torch.rand(C5_CHUNK, generator=g, device=device, dtype=torch.float32)
     x = (cx[which] + sig[which] * torch.randn(C5_CHUNK, generator=g, device=device, dtype=torch.float64)).clamp_(0.0, float(C5_GRID))
     y = (cy[which] + sig[which] * torch.randn(C5_CHUNK, generator=g, device=device, dtype=torch.float64)).clamp_(0.0, float(C5_GRID))
     v = (which.to(torch.float32) / K + 0.05 * torch.randn(C5_CHUNK, generator=g, device=device, dtype=torch.float32))
@@ -583,6 +590,12 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local) if world > 1 else "n/a"
     from pointcloud_raster_b200 import pcr
     K, W = args.steps, args.warmup
+    if args.only_c5:
+        c5 = leg_c5(pcr, D)
+        D.close()
+        if rank == 0:
+            print(json.dumps({"c5": c5}), flush=True)
+        return
     sampler = ClockSampler(local) if rank == 0 else None
 
     p, host0, windows, walls, prof, count_check = leg_headline(pcr, D, K, W)
@@ -817,6 +830,7 @@ def main():
     ap.add_argument("--skip-c5", action="store_true")
     ap.add_argument("--skip-glyphs", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--only-c5", action="store_true", help="development aid: run the config-5 leg alone")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

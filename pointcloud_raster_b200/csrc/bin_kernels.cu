@@ -247,8 +247,18 @@ __global__ void __launch_bounds__(kBinThreads)
 k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restrict__ order,
                  uint32_t* __restrict__ state, size_t cell_base, const __grid_constant__ PassLayout L)
 {
+    // Pages are handed out through a global cursor, NOT by a static stride: persistent CTAs drift apart
+    // (tools/micro/bin_locality.cu: 25 Gpts/s with the static stride, 72 Gpts/s when the pages in flight are
+    // always the contiguous frontier of the bin-ordered list), and only a compact frontier keeps the
+    // records of the bins being folded resident in L2.
     const uint32_t np = min(*pool.next_page, pool.pool_pages);
-    for (uint32_t i = blockIdx.x; i < np; i += gridDim.x) {
+    __shared__ uint32_t s_next;
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(pool.next_page + 2, 1u);
+        __syncthreads();
+        const uint32_t i = s_next;
+        __syncthreads();
+        if (i >= np) break;
         const uint32_t page = order[i];
         const uint32_t cnt = min(pool.page_fill[page], kBinPageEntries);
         const uint32_t e0 = page * kBinPageEntries;
@@ -274,7 +284,7 @@ k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restric
 __global__ void k_bin_reset(const __grid_constant__ BinPool pool, uint32_t* __restrict__ open_page, size_t n_open)
 {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i == 0) *pool.next_page = 0;
+    if (i == 0) { pool.next_page[0] = 0; pool.next_page[2] = 0; }      // pages handed out, accumulate cursor
     for (size_t k = i; k < n_open; k += static_cast<size_t>(gridDim.x) * blockDim.x) open_page[k] = kNoPage;
 }
 

@@ -15,7 +15,7 @@ struct BinPool {
     float*    ent_val[kBinMaxChan];          // [...] channel values, SoA
     uint32_t* page_bin;                      // [pool_pages] bin a page belongs to
     uint32_t* page_fill;                     // [pool_pages] entries written to a page so far
-    uint32_t* next_page;                     // pages handed out so far
+    uint32_t* next_page;                     // [0] pages handed out so far, [1] overflow flag, [2] cursor of the fold
     uint32_t* overflow;                      // set to 1 if the pool ran out (entries were dropped)
     uint32_t  pool_pages;
 };

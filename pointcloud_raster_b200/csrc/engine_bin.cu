@@ -66,9 +66,9 @@ Status Engine::bin_setup(Pass& p)
     for (int c = 0; c < p.layout.n_chan; ++c) CU_TRY(cudaMalloc(&b.pool.ent_val[c], entries * 4));
     CU_TRY(cudaMalloc(&b.pool.page_bin, pages * 4));
     CU_TRY(cudaMalloc(&b.pool.page_fill, pages * 4));
-    CU_TRY(cudaMalloc(&b.pool.next_page, 2 * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&b.pool.next_page, 4 * sizeof(uint32_t)));
     b.pool.overflow = b.pool.next_page + 1;
-    CU_TRY(cudaMemsetAsync(b.pool.next_page, 0, 2 * sizeof(uint32_t), compute_));
+    CU_TRY(cudaMemsetAsync(b.pool.next_page, 0, 4 * sizeof(uint32_t), compute_));
     CU_TRY(cudaMalloc(&b.bin_pages, static_cast<size_t>(b.nbins) * 4));
     CU_TRY(cudaMalloc(&b.bin_first, static_cast<size_t>(b.nbins) * 4));
     CU_TRY(cudaMemsetAsync(b.bin_pages, 0, static_cast<size_t>(b.nbins) * 4, compute_));
