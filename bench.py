@@ -262,15 +262,15 @@ class Dist:
             self.dist.destroy_process_group()
 
 
-def band_to_host(pcr, p, band, device, row0=None, row1=None):
-    """D2H of (a row range of) a finalized band left in HBM by finalize_device()."""
+def band_to_host(pcr, p, band, device, cell0=None, cell1=None):
+    """D2H of (a row-major cell range of) a finalized band left in HBM by finalize_device(); flat array."""
     import ctypes as C
     from pointcloud_raster_b200._lib import lib
     ptr, rows, cols = p.result_band_device_ptr(band)
-    row0, row1 = (0, rows) if row0 is None else (row0, row1)
-    out = np.empty((row1 - row0, cols), np.float32)
+    cell0, cell1 = (0, rows * cols) if cell0 is None else (cell0, cell1)
+    out = np.empty(cell1 - cell0, np.float32)
     if out.size:
-        lib.pcr_mem_copy(C.c_void_p(out.ctypes.data), 0, C.c_void_p(ptr + row0 * cols * 4), 2, out.nbytes, device)
+        lib.pcr_mem_copy(C.c_void_p(out.ctypes.data), 0, C.c_void_p(ptr + cell0 * 4), 2, out.nbytes, device)
     return out
 
 
@@ -466,7 +466,7 @@ def leg_c5(pcr, D):
     p.profile_enable(False)
     sync_all()
     # checks on the distributed bands: every rank sums the row slice it owns
-    r0, r1 = pcr.comm_slice_rows(C5_GRID, D.world, D.rank) if D.world > 1 else (0, C5_GRID)
+    r0, r1 = p.owned_cells()
     cnt = band_to_host(pcr, p, 2, D.local, r0, r1)
     count_sum = D.reduce(float(np.nansum(cnt, dtype=np.float64)), "sum")
     cells_with_data = D.reduce(float(np.count_nonzero(~np.isnan(cnt))), "sum")
@@ -491,14 +491,17 @@ def leg_c5(pcr, D):
            "points": points, "chunks_per_rank": len(mine), "n_gpus": D.world,
            "ms": round(ms, 3), "wall_ms": round(wall, 3), "mpts_per_s": round(points / (ms * 1e-3) / 1e6, 1),
            "scaling": "strong (the same cloud for every N: chunk j depends on j only)",
-           "step": "ingest of every chunk (device-resident) + one finalize_device(); bands stay distributed "
-                   "(every rank holds the row slice it owns)" if D.world > 1 else
-                   "ingest of every chunk (device-resident) + one finalize_device()",
+           "step": "ingest of every chunk (device-resident) + one finalize_device()" + (
+               "; tile-partitioned grid: every rank owns a contiguous range of bins and keeps records for those cells "
+               "only, the binning kernel appends each point's 8-byte entry to its owner's pool over NVLink peer memory "
+               "(the all-to-all), no reduce at finalize; bands stay distributed (every rank holds the cells it owns)"
+               if D.world > 1 and int(os.environ.get("PCR_COMM_LAYOUT", "0")) != 1 else
+               "; replicated partial grids merged at finalize, bands distributed" if D.world > 1 else ""),
            "rank0_accumulate_ms": round(prof["accumulate_ms"], 3), "rank0_sort_or_bin_ms": round(prof["sort_ms"], 3),
            "rank0_push_ms": round(prof.get("push_ms", 0.0), 3), "rank0_merge_finalize_ms": round(prof["finalize_ms"], 3),
            "hbm_frac_algorithmic": round(points * BYTES_PER_POINT / (ms * 1e-3) / 1e9 / (peak * D.world), 4),
            "count_band_sum": count_sum, "count_ok": count_sum == float(points),
-           "max_band_checksum": max_checksum, "cells_with_data": int(cells_with_data), "tiles_active_rank0": int(tiles),
+           "max_band_checksum": round(max_checksum, 2), "cells_with_data": int(cells_with_data), "tiles_active_rank0": int(tiles),
            "host_fed": {"points_per_rank": C5_CHUNK, "ms": round(host_ms, 3),
                         "mpts_per_s": round(C5_CHUNK * D.world / (host_ms * 1e-3) / 1e6, 1),
                         "what": "one 25M-point chunk per rank from pinned host memory: ingest + finalize_device, wall clock"}}

@@ -298,6 +298,10 @@ int pcr_comm_unique_id(void *id128);
 int pcr_comm_slice_rows(int32_t height, int32_t world_size, int32_t rank, int32_t *row0, int32_t *row1);
 int pcr_pipeline_comm_init(pcr_pipeline *p, const void *id128, int32_t rank, int32_t world_size);
 int pcr_pipeline_comm_barrier(pcr_pipeline *p);
+/* Row-major cell range [cell0, cell1) whose finalized bands THIS rank produces: the whole grid on one GPU,
+ * the rank's row slice with replicated partial grids, the cells of its bins with the tile-partitioned layout.
+ * With comm_root_only = 2 a rank's band arrays are valid for exactly this range. */
+int pcr_pipeline_owned_cells(const pcr_pipeline *p, uint64_t *cell0, uint64_t *cell1);
 
 #ifdef __cplusplus
 }

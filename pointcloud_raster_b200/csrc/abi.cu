@@ -290,6 +290,14 @@ int pcr_pipeline_comm_init(pcr_pipeline* p, const void* id128, int32_t rank, int
     return GUARD(finish(eng(p)->comm_init(id128, rank, world_size)));
 }
 
+int pcr_pipeline_owned_cells(const pcr_pipeline* p, uint64_t* cell0, uint64_t* cell1)
+{
+    NEED(p);
+    if (!cell0 || !cell1) return fail(PCR_INVALID_ARGUMENT, "null output pointer");
+    eng(p)->owned_cells(*cell0, *cell1);
+    return PCR_OK;
+}
+
 int pcr_pipeline_comm_barrier(pcr_pipeline* p) { NEED(p); return GUARD(finish(eng(p)->comm_barrier())); }
 
 }  // extern "C"

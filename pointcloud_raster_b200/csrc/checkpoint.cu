@@ -142,6 +142,8 @@ Status Engine::load_state(const std::string& dir)
     // N>1: the files are ONE contribution to the merged state; rank 0 takes them into its partial state
     // (merged into the owners' slices at the next finalize), the other ranks keep the identity — loading
     // them everywhere would count the checkpoint world-size times.
+    if (partition_)
+        return Status::error(PCR_NOT_IMPLEMENTED, "pipeline: load_state is not available with the tile-partitioned multi-GPU layout");
     if (world_ > 1 && rank_ != 0) return Status::success();
     std::vector<uint32_t> touched(std::max(1, n_tiles_));
     CU_TRY(cudaMemcpy(touched.data(), d_touched_, touched.size() * 4, cudaMemcpyDeviceToHost));

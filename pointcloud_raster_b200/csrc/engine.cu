@@ -494,8 +494,9 @@ Status Engine::init_state()
 {
     prof_begin(PROF_INIT, compute_);
     for (Pass& p : passes_) {
+        const size_t n_rec = partition_ ? p.bin.cell1 - p.bin.cell0 : cells_;   // partitioned: my bins' cells only
         for (uint32_t* d : p.d_delta)
-            if (d) { CU_TRY(launch_init_state(compute_, d, cells_, p.layout)); ++launches_; }
+            if (d) { CU_TRY(launch_init_state(compute_, d, n_rec, p.layout)); ++launches_; }
         if (p.d_owned) {
             int r0, r1;
             slice_rows(grid_.height, world_, rank_, r0, r1);
@@ -514,6 +515,8 @@ Status Engine::reset()
 {
     CU_TRY(cudaSetDevice(device_));
     ST_TRY(synchronize());
+    // N>1: collective — the peers' push / scatter kernels write into this rank's buffers
+    if (world_ > 1) ST_TRY(comm_barrier());
     ST_TRY(init_state());
     for (Pass& p : passes_)
         if (p.bin.on) {
@@ -524,7 +527,22 @@ Status Engine::reset()
     collections_ = 0;
     points_ = 0;
     finalized_ = false;
-    return synchronize();
+    ST_TRY(synchronize());
+    if (world_ > 1) ST_TRY(comm_barrier());
+    return Status::success();
+}
+
+// Cells whose finalized bands this rank produces: everything on one GPU, its row slice (replicated partial
+// grids) or the cells of its bins (tile-partitioned layout) on several.
+void Engine::owned_cells(uint64_t& c0, uint64_t& c1) const
+{
+    c0 = 0; c1 = cells_;
+    if (world_ <= 1) return;
+    if (partition_ && !passes_.empty()) { c0 = passes_[0].bin.cell0; c1 = passes_[0].bin.cell1; return; }
+    int r0, r1;
+    slice_rows(grid_.height, world_, rank_, r0, r1);
+    c0 = static_cast<uint64_t>(r0) * grid_.width;
+    c1 = static_cast<uint64_t>(r1) * grid_.width;
 }
 
 Status Engine::synchronize()

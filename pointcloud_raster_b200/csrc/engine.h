@@ -71,6 +71,11 @@ struct BinState {
     unsigned grid = 0;
     uint64_t pending = 0;           // points appended since the last flush (upper bound of entries)
     uint64_t capacity = 0;          // points the pool takes whatever their distribution over the bins
+    // N>1, tile-partitioned layout (engine_part.cu): owner of a bin = bin / bins_per_owner; this rank holds
+    // records for cells [cell0, cell1) only and appends to the owners' pools over peer memory
+    uint32_t bins_per_owner = 0;
+    size_t cell0 = 0, cell1 = 0;
+    BinPool peer_pool[kMaxParts] = {};
 };
 
 // One fused pass: every reduction in it shares the glyph footprint.
@@ -178,6 +183,7 @@ public:
 
     Status comm_init(const void* id128, int rank, int world);
     Status comm_barrier();
+    void owned_cells(uint64_t& c0, uint64_t& c1) const;
 
 private:
     Engine() = default;
@@ -205,6 +211,12 @@ private:
     Status peer_map();               // exchange CUDA IPC handles, map every rank's buffers
     void peer_unmap();
     void peer_close_handles();
+    Status ipc_exchange(const std::vector<void*>& mine, std::vector<std::vector<void*>>& all);
+    Status nccl_allreduce_min_u32(uint32_t* d, size_t count);
+    bool partition_wanted() const;
+    Status partition_setup();
+    Status part_append(Pass& p, const uint8_t* mask, const double* dx, const double* dy, const ChannelPtrs& ch, size_t n);
+    Status finalize_multi_part();
     int channel_slot(const std::string& name);
 
     // profiling helpers
@@ -321,6 +333,9 @@ private:
     int rank_ = 0, world_ = 1;
     // peer-memory path: every rank's state / touched / bands / flags mapped into this process
     bool peer_ok_ = false;
+    bool partition_ = false;          // tile-partitioned grid + point exchange instead of partial grids + merge
+    uint32_t part_waited_epoch_ = 0;  // last epoch whose "pool is empty again" flags this rank has awaited
+    std::vector<void*> ipc_opened_;   // peer mappings opened by ipc_exchange
     int comm_layout_ = 0;             // 0 auto, 1 replicated partial grids, 2 tile-partitioned
     int comm_mode_ = 0;               // 0 auto (peer memory when every pair has P2P), 1 NCCL, 2 peer
     bool gather_root_only_ = false;

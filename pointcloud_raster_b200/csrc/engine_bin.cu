@@ -97,6 +97,7 @@ void Engine::bin_free(Pass& p)
 Status Engine::bin_append(Pass& p, const uint8_t* mask, const double* dx, const double* dy, const ChannelPtrs& ch, size_t n)
 {
     BinState& b = p.bin;
+    if (partition_) return part_append(p, mask, dx, dy, ch, n);
     size_t done = 0;
     while (done < n) {
         if (b.pending >= b.capacity) ST_TRY(bin_flush(p));
@@ -135,6 +136,7 @@ Status Engine::bin_flush(Pass& p)
 
 Status Engine::bin_flush_all()
 {
+    if (partition_) return Status::success();      // folded inside finalize_multi_part, behind the peers' flags
     for (Pass& p : passes_) ST_TRY(bin_flush(p));
     return Status::success();
 }

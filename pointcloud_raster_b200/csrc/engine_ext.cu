@@ -175,8 +175,12 @@ Status Engine::comm_init(const void* id128, int rank, int world)
     CU_TRY(cudaMalloc(&d_touched_all_, std::max(1, n_tiles_) * sizeof(uint32_t)));
     if (comm_mode_ != 1) {
         Status s = peer_map();
-        if (!s.ok() && comm_mode_ == 2) return s;     // peer memory was demanded
+        if (!s.ok() && (comm_mode_ == 2 || comm_layout_ == 2)) return s;     // peer memory was demanded
     }
+    if (comm_layout_ == 2 && !partition_)
+        return Status::error(PCR_INVALID_ARGUMENT,
+                             "pipeline: the tile-partitioned layout (comm_layout = 2) needs peer memory between all GPUs and "
+                             "tile-binned Point passes only (point_kernel = 3, or a grid whose records exceed 256 MB)");
     return Status::success();
 }
 
@@ -189,6 +193,7 @@ Status Engine::comm_init(const void* id128, int rank, int world)
 Status Engine::peer_map()
 {
     peer_ok_ = false;
+    const bool part = partition_wanted();      // tile-partitioned layout: no partial grids, no combine buffers
     int* d_flag = nullptr;
     CU_TRY(cudaMalloc(&d_flag, sizeof(int) * std::max(world_, 2)));
     // every rank must reach every collective below whatever happens locally: failures are recorded and
@@ -236,6 +241,7 @@ Status Engine::peer_map()
             CU_TRY(cudaMemsetAsync(d_flags_, 0, (2 * kMaxParts + 4) * sizeof(uint32_t), compute_));
         }
         for (Pass& p : passes_) {
+            if (part) break;
             const size_t W = p.layout.width;
             if (!p.d_combined) CU_TRY(cudaMalloc(&p.d_combined, static_cast<size_t>(world_) * max_slice * W * 4));
             if (!p.d_delta[1]) {
@@ -266,14 +272,15 @@ Status Engine::peer_map()
     if (!local.ok()) cudaGetLastError();
 
     // 3. handles: [pass combine buffers..., touched staging, out, flags]
-    const size_t n_buf = passes_.size() + 3;
+    const size_t n_comb = part ? 0 : passes_.size();
+    const size_t n_buf = n_comb + 3;
     std::vector<cudaIpcMemHandle_t> mine(n_buf);
     if (local.ok()) {
         auto get = [&]() -> Status {
-            for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(cudaIpcGetMemHandle(&mine[i], passes_[i].d_combined));
-            CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size()], d_touched_stage_));
-            CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 1], d_out_));
-            CU_TRY(cudaIpcGetMemHandle(&mine[passes_.size() + 2], d_flags_));
+            for (size_t i = 0; i < n_comb; ++i) CU_TRY(cudaIpcGetMemHandle(&mine[i], passes_[i].d_combined));
+            CU_TRY(cudaIpcGetMemHandle(&mine[n_comb], d_touched_stage_));
+            CU_TRY(cudaIpcGetMemHandle(&mine[n_comb + 1], d_out_));
+            CU_TRY(cudaIpcGetMemHandle(&mine[n_comb + 2], d_flags_));
             return Status::success();
         };
         local = get();
@@ -308,10 +315,10 @@ Status Engine::peer_map()
             auto open = [&](const cudaIpcMemHandle_t& hh, void** out) {
                 return cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess);
             };
-            for (size_t i = 0; i < passes_.size(); ++i) CU_TRY(open(h[i], reinterpret_cast<void**>(&pb.combined[i])));
-            CU_TRY(open(h[passes_.size()], reinterpret_cast<void**>(&pb.touched_stage)));
-            CU_TRY(open(h[passes_.size() + 1], reinterpret_cast<void**>(&pb.out)));
-            CU_TRY(open(h[passes_.size() + 2], reinterpret_cast<void**>(&pb.flags)));
+            for (size_t i = 0; i < n_comb; ++i) CU_TRY(open(h[i], reinterpret_cast<void**>(&pb.combined[i])));
+            CU_TRY(open(h[n_comb], reinterpret_cast<void**>(&pb.touched_stage)));
+            CU_TRY(open(h[n_comb + 1], reinterpret_cast<void**>(&pb.out)));
+            CU_TRY(open(h[n_comb + 2], reinterpret_cast<void**>(&pb.flags)));
         }
         return Status::success();
     };
@@ -324,12 +331,67 @@ Status Engine::peer_map()
         return opened.ok() ? Status::error(PCR_CUDA_ERROR, "pipeline: a peer rank could not map the combine buffers") : opened;
     }
     peer_ok_ = true;
-    delta_mode_ = true;
+    delta_mode_ = !part;
+    if (part) return partition_setup();
+    return Status::success();
+}
+
+// Collective: every rank hands in the same number of device allocations (nullptr allowed, at the same
+// positions on every rank) and gets everybody's back, mapped into its address space (its own as they are).
+Status Engine::ipc_exchange(const std::vector<void*>& mine, std::vector<std::vector<void*>>& all)
+{
+    const size_t n = mine.size();
+    std::vector<cudaIpcMemHandle_t> h(n);
+    Status local = Status::success();
+    for (size_t i = 0; i < n && local.ok(); ++i) {
+        std::memset(&h[i], 0, sizeof h[i]);
+        if (!mine[i]) continue;
+        const cudaError_t e = cudaIpcGetMemHandle(&h[i], mine[i]);
+        if (e != cudaSuccess) local = Status::error(PCR_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e) + " (cudaIpcGetMemHandle)");
+    }
+    const size_t bytes = n * sizeof(cudaIpcMemHandle_t);
+    std::vector<cudaIpcMemHandle_t> got(n * world_);
+    unsigned char* d_h = nullptr;
+    CU_TRY(cudaMalloc(&d_h, std::max<size_t>(bytes, 16) * world_));
+    CU_TRY(cudaMemcpyAsync(d_h + bytes * rank_, h.data(), bytes, cudaMemcpyHostToDevice, compute_));
+    NC_TRY(nccl_->AllGather(d_h + bytes * rank_, d_h, bytes, NcclApi::kUint8, comm_, compute_));
+    CU_TRY(cudaMemcpyAsync(got.data(), d_h, bytes * world_, cudaMemcpyDeviceToHost, compute_));
+    CU_TRY(cudaStreamSynchronize(compute_));
+    cudaFree(d_h);
+    all.assign(world_, std::vector<void*>(n, nullptr));
+    for (int k = 0; k < world_ && local.ok(); ++k)
+        for (size_t i = 0; i < n && local.ok(); ++i) {
+            if (!mine[i]) continue;
+            if (k == rank_) { all[k][i] = mine[i]; continue; }
+            const cudaError_t e = cudaIpcOpenMemHandle(&all[k][i], got[n * k + i], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) local = Status::error(PCR_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e) + " (cudaIpcOpenMemHandle)");
+            else ipc_opened_.push_back(all[k][i]);
+        }
+    if (!local.ok()) cudaGetLastError();
+    // agree on the outcome: a rank that failed must not leave the others with half a mapping
+    uint32_t* d_ok = nullptr;
+    CU_TRY(cudaMalloc(&d_ok, 4));
+    const uint32_t mine_ok = local.ok() ? 1u : 0u;
+    uint32_t all_ok = 0;
+    CU_TRY(cudaMemcpyAsync(d_ok, &mine_ok, 4, cudaMemcpyHostToDevice, compute_));
+    ST_TRY(nccl_allreduce_min_u32(d_ok, 1));
+    CU_TRY(cudaMemcpyAsync(&all_ok, d_ok, 4, cudaMemcpyDeviceToHost, compute_));
+    CU_TRY(cudaStreamSynchronize(compute_));
+    cudaFree(d_ok);
+    if (!all_ok) return local.ok() ? Status::error(PCR_CUDA_ERROR, "pipeline: a peer rank could not map the entry pools") : local;
+    return Status::success();
+}
+
+Status Engine::nccl_allreduce_min_u32(uint32_t* d, size_t count)
+{
+    NC_TRY(nccl_->AllReduce(d, d, count, NcclApi::kUint32, /*ncclMin*/ 3, comm_, compute_));
     return Status::success();
 }
 
 void Engine::peer_close_handles()
 {
+    for (void* q : ipc_opened_) cudaIpcCloseMemHandle(q);
+    ipc_opened_.clear();
     for (int k = 0; k < world_; ++k) {
         if (k == rank_) continue;
         for (uint32_t* p : peer_[k].combined) if (p) cudaIpcCloseMemHandle(p);
@@ -496,6 +558,7 @@ Status Engine::peer_quiesce()
 
 Status Engine::finalize_multi()
 {
+    if (partition_) return finalize_multi_part();
     return peer_ok_ ? finalize_multi_peer() : finalize_multi_nccl();
 }
 

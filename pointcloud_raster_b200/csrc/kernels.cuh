@@ -125,6 +125,10 @@ cudaError_t launch_push_slices(cudaStream_t s, uint32_t* state, uint32_t* touche
                                const GridParams& g, const PassLayout& L, const PushTargets& pt,
                                const PeerSync& ps, bool push_touched, bool signal, bool reset, int sm_count);
 
+// partition mode: my touched-tile flags into everyone's staging (slot = my rank), then phase 0 of `epoch`
+// on every rank ("everything this stream wrote into your memory so far has landed")
+cudaError_t launch_push_touched(cudaStream_t s, const uint32_t* touched, int n_tiles, const PushTargets& pt,
+                                const PeerFlags& pf, uint32_t epoch);
 // store `epoch` into slot (phase, my rank) of every rank's flag array (system-scope release)
 cudaError_t launch_peer_signal(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch);
 // wait until every rank's slot of `phase` in MY flag array has reached `epoch`

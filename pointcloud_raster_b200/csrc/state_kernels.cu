@@ -361,6 +361,21 @@ __global__ void k_peer_signal(const __grid_constant__ PeerFlags pf, int phase, u
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(slot), "r"(epoch) : "memory");
 }
 
+__global__ void k_push_touched(const uint32_t* __restrict__ touched, int n_tiles, const __grid_constant__ PushTargets pt,
+                               const __grid_constant__ PeerFlags pf, uint32_t epoch)
+{
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        const uint32_t v = touched[t];
+        for (int k = 0; k < pf.n; ++k) pt.touched_stage[k][static_cast<size_t>(pf.rank) * n_tiles + t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < pf.n) {
+        __threadfence_system();      // the stores above, and everything earlier kernels of this stream posted
+        uint32_t* slot = pf.flags[threadIdx.x] + pf.rank;                     // phase 0
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(slot), "r"(epoch) : "memory");
+    }
+}
+
 __global__ void k_peer_wait(const __grid_constant__ PeerFlags pf, int phase, uint32_t epoch)
 {
     const int k = threadIdx.x;
@@ -485,6 +500,13 @@ cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t
     case 8: k_finalize_peer<8><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps, accum); break;
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_push_touched(cudaStream_t s, const uint32_t* touched, int n_tiles, const PushTargets& pt,
+                                const PeerFlags& pf, uint32_t epoch)
+{
+    k_push_touched<<<1, 256, 0, s>>>(touched, n_tiles, pt, pf, epoch);
     return cudaGetLastError();
 }
 

@@ -981,6 +981,13 @@ class Pipeline:
     def comm_barrier(self):
         check(lib.pcr_pipeline_comm_barrier(self._h))
 
+    def owned_cells(self):
+        """Row-major cell range [cell0, cell1) whose finalized bands this rank produces (N>1; the whole grid on
+        one GPU).  With comm_root_only = 2 the rank's band arrays are valid for exactly this range."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib.pcr_pipeline_owned_cells(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
 
 def diag_red_ceiling(points=5_000_000, cells=1_000_000, with_loads=False, reps=20, device=0) -> float:
     """Median microseconds the GPU needs for the Point kernel's reductions alone (measurement aid)."""

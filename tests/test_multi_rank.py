@@ -218,3 +218,98 @@ def test_multi_gpu_finalize_matches_oracle(gpu_pcr, oracle, deterministic, comm_
     gd = grid_desc(gc)
     ref = oracle.run(gd, [(x, y, ch)], specs)
     compare_bands(oracle, gd, [(x, y, ch)], specs, ref, per_rank[0], f"{world} GPUs", device_weights=True)
+
+
+# ---- tile-partitioned grid + point exchange (comm_layout = 2) -----------------------------------------
+def _part_case(pcr):
+    from util import make_grid, spec
+    w, h = 333, 257
+    gc = make_grid(pcr, w, h, tile=64)
+    rng = np.random.default_rng(91)
+    n = 500_000
+    x, y = rng.uniform(-2, w + 2, n), rng.uniform(-2, h * 0.7, n)           # the north tiles stay untouched
+    ch = {"value": rng.normal(0, 3, n).astype(np.float32), "other": rng.uniform(0, 1, n).astype(np.float32)}
+    R = pcr.ReductionType
+    specs = [spec(pcr, "value", t) for t in (R.Sum, R.Max, R.Min, R.Average, R.Count)] + [spec(pcr, "other", R.Sum)]
+    return gc, x, y, ch, specs
+
+
+def _part_worker(rank, world, id_path, out_dir, root_only):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import time
+    from pointcloud_raster_b200 import pcr
+    from util import cloud as mk
+    if rank == 0:
+        open(id_path + ".tmp", "wb").write(pcr.comm_unique_id())
+        os.rename(id_path + ".tmp", id_path)
+    while not os.path.exists(id_path):
+        time.sleep(0.01)
+    uid = open(id_path, "rb").read()
+    gc, x, y, ch, specs = _part_case(pcr)
+    n = len(x)
+    cfg = pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = specs; cfg.exec_mode = pcr.ExecutionMode.GPU
+    cfg.cuda_device_id = rank
+    cfg.point_kernel = 3; cfg.bin_cells_log2 = 9; cfg.comm_layout = 2; cfg.comm_root_only = root_only
+    p = pcr.Pipeline.create(cfg)
+    assert p is not None
+    p.comm_init(uid, rank, world)
+    # uneven shards, three ingest + finalize rounds (the exchange and the pools must be reusable), the last
+    # round with two ingests before the finalize; rank 0 ingests nothing in round 1
+    cut = np.linspace(0, n, 3 * world + 1).astype(int)
+    for r in range(3):
+        a, b = cut[r * world + rank], cut[r * world + rank + 1]
+        if not (r == 1 and rank == 0):
+            m = (a + b) // 2 if r == 2 else b
+            p.ingest(mk(pcr, x[a:m], y[a:m], {k: v[a:m] for k, v in ch.items()}))
+            if r == 2:
+                p.ingest(mk(pcr, x[m:b], y[m:b], {k: v[m:b] for k, v in ch.items()}).to_device(rank))
+        p.finalize()
+    c0, c1 = p.owned_cells()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), np.array([c0, c1]),
+             *[np.array(p.result().band_array(i)) for i in range(len(specs))])
+    p.comm_barrier()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("root_only", [0, 2], ids=["bands_everywhere", "bands_distributed"])
+def test_multi_gpu_partitioned_grid_point_exchange(gpu_pcr, oracle, root_only):
+    if gpu_pcr.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import multiprocessing as mp
+    from util import compare_bands, grid_desc
+    world = min(gpu_pcr.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as d:
+        procs = [ctx.Process(target=_part_worker, args=(r, world, os.path.join(d, "id"), d, root_only)) for r in range(world)]
+        for pr in procs: pr.start()
+        for pr in procs: pr.join(300)
+        assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+        ranks = []
+        for r in range(world):
+            z = np.load(os.path.join(d, f"rank{r}.npz"))
+            arrs = [z[k] for k in sorted(z.files, key=lambda s: int(s.split("_")[1]))]
+            ranks.append((arrs[0], arrs[1:]))
+    pcr = gpu_pcr
+    gc, x, y, ch, specs = _part_case(pcr)
+    n = len(x)
+    # points rank 0 skipped in round 1 were never ingested
+    cut = np.linspace(0, n, 3 * world + 1).astype(int)
+    keep = np.ones(n, bool)
+    keep[cut[world]:cut[world + 1]] = False
+    xs, ys, chs = x[keep], y[keep], {k: v[keep] for k, v in ch.items()}
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, [(xs, ys, chs)], specs)
+    # ownership: contiguous cell ranges that tile the grid
+    edges = sorted((int(o[0]), int(o[1])) for o, _ in ranks)
+    assert edges[0][0] == 0 and edges[-1][1] == gc.width * gc.height
+    assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+    if root_only == 0:
+        for _, bands in ranks:                            # every rank ends with the same complete bands
+            compare_bands(oracle, gd, [(xs, ys, chs)], specs, ref, bands, f"partitioned, {world} GPUs")
+    else:                                                 # every rank holds exactly the cells it owns
+        got = [np.full(gc.width * gc.height, np.nan, np.float32) for _ in specs]
+        for (c0, c1), bands in ranks:
+            for g, b in zip(got, bands):
+                g[int(c0):int(c1)] = b.reshape(-1)[int(c0):int(c1)]
+        got = [g.reshape(gc.height, gc.width) for g in got]
+        compare_bands(oracle, gd, [(xs, ys, chs)], specs, ref, got, f"partitioned + distributed bands, {world} GPUs")
