@@ -551,6 +551,7 @@ Status Engine::synchronize()
     ST_TRY(peer_quiesce());
     CU_TRY(cudaStreamSynchronize(copy_));
     CU_TRY(cudaStreamSynchronize(compute_));
+    if (push_) CU_TRY(cudaStreamSynchronize(push_));
     CU_TRY(cudaStreamSynchronize(fin_));
     fin_pending_ = false;
     return Status::success();
@@ -569,6 +570,7 @@ Engine::~Engine()
         cudaSetDevice(device_);
         if (copy_) cudaStreamSynchronize(copy_);
         if (compute_) cudaStreamSynchronize(compute_);
+        if (push_) cudaStreamSynchronize(push_);
         if (fin_) cudaStreamSynchronize(fin_);
     }
     peer_unmap();
@@ -606,6 +608,7 @@ Engine::~Engine()
     if (compute_) cudaStreamDestroy(compute_);
     if (copy_) cudaStreamDestroy(copy_);
     if (fin_) cudaStreamDestroy(fin_);
+    if (push_) cudaStreamDestroy(push_);
 }
 
 // Pipeline::validate, src/engine/pipeline.cpp:1306-1338

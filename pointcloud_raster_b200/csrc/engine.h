@@ -271,6 +271,7 @@ private:
     // multi-GPU finalize: the merge/finalize kernels run on their own stream behind the push, so the
     // next ingest's kernels (compute stream) overlap the wait for the peers
     cudaStream_t fin_ = nullptr;
+    cudaStream_t push_ = nullptr;     // N>1 delta epochs: the slice push, between the ingest and the merge streams
     cudaEvent_t e_pushed_ = nullptr, e_fin_ = nullptr;
     bool fin_pending_ = false;
     int band_copy_ = 0;               // pcr_pipeline_desc::comm_band_copy

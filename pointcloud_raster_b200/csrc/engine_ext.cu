@@ -243,7 +243,7 @@ Status Engine::peer_map()
         for (Pass& p : passes_) {
             if (part) break;
             const size_t W = p.layout.width;
-            if (!p.d_combined) CU_TRY(cudaMalloc(&p.d_combined, static_cast<size_t>(world_) * max_slice * W * 4));
+            if (!p.d_combined) CU_TRY(cudaMalloc(&p.d_combined, 2 * static_cast<size_t>(world_) * max_slice * W * 4));   // [epoch parity][rank][cell]
             if (!p.d_delta[1]) {
                 CU_TRY(cudaMalloc(&p.d_delta[1], cells_ * W * 4));
                 CU_TRY(launch_init_state(compute_, p.d_delta[1], cells_, p.layout));
@@ -262,10 +262,15 @@ Status Engine::peer_map()
             CU_TRY(cudaMemsetAsync(d_touched_merged_, 0, nt * 4, compute_));
         }
         if (!d_touched_stage_) {
-            CU_TRY(cudaMalloc(&d_touched_stage_, static_cast<size_t>(world_) * nt * 4));
-            CU_TRY(cudaMemsetAsync(d_touched_stage_, 0, static_cast<size_t>(world_) * nt * 4, compute_));
+            CU_TRY(cudaMalloc(&d_touched_stage_, 2 * static_cast<size_t>(world_) * nt * 4));                             // [epoch parity][rank][tile]
+            CU_TRY(cudaMemsetAsync(d_touched_stage_, 0, 2 * static_cast<size_t>(world_) * nt * 4, compute_));
         }
         if (!e_delta_) CU_TRY(cudaEventCreateWithFlags(&e_delta_, cudaEventDisableTiming));
+        if (!push_) {
+            int lo = 0, hi = 0;
+            CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU_TRY(cudaStreamCreateWithPriority(&push_, cudaStreamNonBlocking, hi));
+        }
         return Status::success();
     };
     Status local = alloc_local();
@@ -419,39 +424,40 @@ void Engine::peer_unmap()
     peer_ok_ = false;
 }
 
-// N>1 finalize over peer memory, "delta epochs".  No host sync anywhere; two streams.
+// N>1 finalize over peer memory, "delta epochs".  No host sync anywhere; three streams.
 //
 // What a rank accumulates between two finalizes is a DELTA (records start from the identity); the rank
 // that owns a row slice keeps the running merge of everybody's deltas (d_owned).  Because Op::merge is
 // a commutative monoid (builtin_ops.h:15,28,41,54,67,95-97) the result is the same state a single
-// cumulative grid would hold, and the delta buffers are double-buffered, so NOTHING of a finalize sits
-// on the ingest stream: the kernels of the next ingest start at once, into the other delta buffer.
+// cumulative grid would hold.  Delta buffers, combine buffers and touched staging are all double-buffered
+// by epoch parity, so NOTHING of a finalize sits on the ingest stream and push(e+1) runs under merge(e):
 //
-// Compute stream: [ingest kernels of epoch e] -> event "delta e complete" -> [ingest kernels of e+1 ...]
-// Finalize stream (highest priority), behind that event:
-//   k_peer_wait     the peers are done reading their combine buffers (phase 1 of epoch e-1)
+// compute stream  [ingest kernels of epoch e] -> event "delta e complete" -> [ingest kernels of e+1 ...]
+// push stream     behind that event:
+//   k_peer_wait     the peers are done reading the combine buffers of this parity (phase 1 of epoch e-2)
 //   k_push_slices   persistent copy kernel: every record of the delta goes into the combine buffer of the
 //                   rank that owns its row (posted NVLink writes; a local copy for my own slice) and is put
 //                   back to the identity behind the copy; my touched-tile flags go into everyone's staging;
 //                   the last CTA releases phase 0 on every rank
+// merge stream    (highest priority) behind my own push:
 //   k_peer_wait_merge_touched   every rank's push has landed here; OR the touched flags into the merged set
 //   k_finalize_peer persistent kernel: owned = merge(owned, delta of rank 0, 1, ...) in rank order, finalize,
 //                   store the bands into my array and the peers' arrays; the last CTA releases phase 1
 //   (k_peer_wait)   peer_quiesce(): phase 1 from everyone, before the host reads the bands.
-// The compute stream waits for the finalize stream only where it must: before it accumulates into the
-// delta buffer whose push was enqueued one finalize earlier, before a D2H of the bands, in synchronize()
-// and in timer_end().
+// The compute stream waits for the others only where it must: before it accumulates into the delta buffer
+// whose push was enqueued one finalize earlier, before a D2H of the bands, in synchronize() and timer_end().
 Status Engine::finalize_multi_peer()
 {
     ++epoch_;
+    const int par = static_cast<int>(epoch_ & 1u);
     PeerSync ps{};
     ps.pf.n = world_; ps.pf.rank = rank_;
     ps.pt.n = world_;
     ps.epoch = epoch_;
-    ps.done_counter = reinterpret_cast<unsigned int*>(d_flags_ + 2 * kMaxParts);
+    const size_t nt = std::max(1, n_tiles_);
     for (int k = 0; k < world_; ++k) {
         ps.pf.flags[k] = peer_[k].flags;
-        ps.pt.touched[k] = d_touched_stage_ + static_cast<size_t>(k) * n_tiles_;   // local staging
+        ps.pt.touched[k] = d_touched_stage_ + (static_cast<size_t>(par) * world_ + k) * nt;   // local staging of this parity
     }
     const size_t rows_per = (static_cast<size_t>(grid_.height) + world_ - 1) / world_;
     const size_t max_slice = rows_per * static_cast<size_t>(grid_.width);
@@ -469,26 +475,33 @@ Status Engine::finalize_multi_peer()
     for (Pass& p : passes_) p.d_state = p.d_delta[cur_];
     d_touched_ = d_touched_buf_[cur_];
 
-    // ---- finalize stream: push the delta, wait for the peers' pushes, merge, finalize, store the bands ----
-    CU_TRY(cudaStreamWaitEvent(fin_, e_delta_, 0));
+    // ---- push stream ----
+    CU_TRY(cudaStreamWaitEvent(push_, e_delta_, 0));
     ps.waited = 1;
-    prof_begin(PROF_PUSH, fin_);
-    // The peers' combine buffers may still be read by their previous merge: one small kernel waits for
-    // their "done" flags of the previous epoch (instead of every CTA of the push polling them).
-    if (epoch_ > 1) { CU_TRY(launch_peer_wait(fin_, ps.pf, 1, epoch_ - 1)); ++launches_; }
-    if (passes_.empty()) CU_TRY(launch_peer_signal(fin_, ps.pf, 0, epoch_));
+    ps.done_counter = reinterpret_cast<unsigned int*>(d_flags_ + 2 * kMaxParts);
+    prof_begin(PROF_PUSH, push_);
+    // The combine buffers of this parity were last read by the peers' merge of epoch e-2.
+    if (epoch_ > 2) { CU_TRY(launch_peer_wait(push_, ps.pf, 1, epoch_ - 2)); ++launches_; }
+    if (passes_.empty()) CU_TRY(launch_peer_signal(push_, ps.pf, 0, epoch_));
     for (size_t i = 0; i < passes_.size(); ++i) {
+        const size_t W = passes_[i].layout.width;
         PushTargets pt{};
-        for (int k = 0; k < world_; ++k) { pt.combined[k] = peer_[k].combined[i]; pt.touched_stage[k] = peer_[k].touched_stage; }
+        for (int k = 0; k < world_; ++k) {
+            pt.combined[k] = peer_[k].combined[i] + static_cast<size_t>(par) * world_ * max_slice * W;
+            pt.touched_stage[k] = peer_[k].touched_stage + static_cast<size_t>(par) * world_ * nt;
+        }
         pt.rows_per = static_cast<int>(rows_per);
         pt.max_slice_cells = max_slice;
-        CU_TRY(launch_push_slices(fin_, passes_[i].d_delta[old], d_touched_buf_[old], n_tiles_, gp_, passes_[i].layout, pt, ps,
+        CU_TRY(launch_push_slices(push_, passes_[i].d_delta[old], d_touched_buf_[old], n_tiles_, gp_, passes_[i].layout, pt, ps,
                                   i + 1 == passes_.size(), i + 1 == passes_.size(), true, sm_count_));
         ++launches_;
     }
-    prof_end(fin_);
-    CU_TRY(cudaEventRecord(e_pushed_, fin_));
+    prof_end(push_);
+    CU_TRY(cudaEventRecord(e_pushed_, push_));
 
+    // ---- merge stream ----
+    CU_TRY(cudaStreamWaitEvent(fin_, e_pushed_, 0));
+    ps.done_counter = reinterpret_cast<unsigned int*>(d_flags_ + 2 * kMaxParts + 1);     // the two kernels may overlap
     prof_begin(PROF_FIN, fin_);
     // One small kernel holds the stream until every peer's push has landed (the merge kernel's own CTAs
     // would all spin on the same flags and occupy the SMs the next ingest wants) and ORs the ranks'
@@ -519,7 +532,8 @@ Status Engine::finalize_multi_peer()
         StateParts parts{};
         parts.n = world_ + 1;
         parts.part[0] = p.d_owned;
-        for (int k = 0; k < world_; ++k) parts.part[k + 1] = p.d_combined + static_cast<size_t>(k) * max_slice * W;
+        for (int k = 0; k < world_; ++k)
+            parts.part[k + 1] = p.d_combined + (static_cast<size_t>(par) * world_ + k) * max_slice * W;
         ps.signal_begin = 0;
         ps.signal_end = !bulk_bands && i + 1 == passes_.size();
         CU_TRY(launch_finalize_peer(fin_, parts, my0, my0, my_cells, outs, cells_, gp_, p.layout, p.fin, ps, p.d_owned, sm_count_));
@@ -537,8 +551,9 @@ Status Engine::finalize_multi_peer()
     prof_end(fin_);
     CU_TRY(cudaEventRecord(e_fin_, fin_));
     fin_pending_ = true;
-    // Not awaited here: the peers' "done" flags of this epoch.  They are awaited by the next push (before
-    // it overwrites the peers' combine buffers) and by peer_quiesce() before the host looks at the bands.
+    // Not awaited here: the peers' "done" flags of this epoch.  They are awaited by the push after next
+    // (before it overwrites the peers' combine buffers of this parity) and by peer_quiesce() before the
+    // host looks at the bands.
     return Status::success();
 }
 
