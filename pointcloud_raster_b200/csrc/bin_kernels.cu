@@ -31,8 +31,8 @@ using point_impl::RecordShape;
 using point_impl::pick;
 using point_impl::update_record;
 
-constexpr int kBinThreads = 256;
-constexpr int kBinPts = 16;                               // points per thread and chunk
+constexpr int kBinThreads = 512;                          // 2 CTAs per SM (<= 64 registers): 32 warps hide the
+constexpr int kBinPts = 8;                                // load -> sort -> store phases of each other
 constexpr int kBinChunk = kBinThreads * kBinPts;          // 4096 = kBinPageEntries
 static_assert(kBinChunk == static_cast<int>(kBinPageEntries), "a chunk's run must fit two pages");
 constexpr uint32_t kNoPage = 0xffffffffu;
@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t* s_hist, uint
     if (warp == 0) {
         uint32_t w = lane < kBinThreads / 32 ? s_warp[lane] : 0u;
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
+        for (int d = 1; d < kBinThreads / 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, w, d);
             if (lane >= d) w += t;
         }
@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t* s_hist, uint
 // One CTA = a persistent worker with its own page chain per bin (open_page / open_fill rows in global
 // memory survive from launch to launch, so a chain's only partly filled page is its last one).
 template <int NCH, bool EXACT>
-__global__ void __launch_bounds__(kBinThreads)
+__global__ void __launch_bounds__(kBinThreads, 2)
 k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
               const __grid_constant__ ChannelPtrs ch, size_t n, const __grid_constant__ GridParams g,
               const __grid_constant__ BinTargets bt, uint32_t* __restrict__ touched)
@@ -89,12 +89,15 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
     const int nbins = bt.nbins;
     uint32_t* s_hist   = reinterpret_cast<uint32_t*>(smem_raw);          // [nbins]  points of this chunk per bin
     uint32_t* s_prefix = s_hist + nbins;                                  // [nbins]  exclusive scan
-    uint32_t* s_seg_a  = s_prefix + nbins;                                // [nbins]  entry index of rank 0 (first page)
-    uint32_t* s_len_a  = s_seg_a + nbins;                                 // [nbins]  ranks served by the first page
-    uint32_t* s_seg_b  = s_len_a + nbins;                                 // [nbins]  entry index of rank len_a (second page)
-    uint32_t* s_pool   = s_seg_b + nbins;                                 // [nbins]  which pool (owner rank) the bin lives in
-    uint32_t* s_warp   = s_pool + nbins;                                  // [8]
-    uint32_t* st_pos   = s_warp + 8;                                      // [chunk]  destination entry index
+    // per bin, one 128-bit load in the sort step: {prefix, ranks served by the first page, entry index of
+    // rank 0 in the first page, entry index of rank 0 in the second page minus len_a | owner << 28 ... }
+    const int nb4 = (2 * nbins + 3) & ~3;                                 // keep the table 16-byte aligned
+    uint4*    s_tab    = reinterpret_cast<uint4*>(s_hist + nb4);          // [nbins]  {prefix, len_a, seg_a, seg_b - len_a}
+    uint32_t* s_pool   = reinterpret_cast<uint32_t*>(s_tab + nbins);      // [nbins]  which pool (owner rank) the bin lives in
+    uint32_t* s_open_page = s_pool + nbins;                               // [nbins]  this CTA's page chains, kept in shared
+    uint32_t* s_open_fill = s_open_page + nbins;                          // [nbins]  memory for the life of the launch
+    uint32_t* s_warp   = s_open_fill + nbins;                             // [32]
+    uint32_t* st_pos   = s_warp + 32;                                     // [chunk]  destination entry index
     uint32_t* st_cell  = st_pos + kBinChunk;                              // [chunk]
     float*    st_val   = reinterpret_cast<float*>(st_cell + kBinChunk);   // [NCH][chunk]
     uint8_t*  st_pool  = reinterpret_cast<uint8_t*>(st_val + static_cast<size_t>(NCH) * kBinChunk);   // [chunk]
@@ -104,7 +107,9 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
     uint32_t* my_open_fill = bt.open_fill + static_cast<size_t>(blockIdx.x) * nbins;
     const size_t nchunks = (n + kBinChunk - 1) / kBinChunk;
     const bool multi_tile = g.tiles_x * g.tiles_y > 1;
+    const bool multi_pool = bt.bin_owner_shift >= 0;
     bool any_valid = false;
+    for (int b = tid; b < nbins; b += kBinThreads) { s_open_page[b] = my_open_page[b]; s_open_fill[b] = my_open_fill[b]; }
 
     for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         for (int b = tid; b < nbins; b += kBinThreads) s_hist[b] = 0;
@@ -149,12 +154,13 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
 
         // ---- where does each bin's run go?  (page chain of this CTA; at most two pages per run) ----
         const uint32_t total = block_scan_bins(s_hist, s_prefix, nbins, s_warp);
+        __syncthreads();                                   // s_prefix[b] is read by another thread than its writer
         for (int b = tid; b < nbins; b += kBinThreads) {
             const uint32_t cnt = s_hist[b];
             if (cnt == 0) continue;
             const int owner = bt.bin_owner_shift >= 0 ? static_cast<int>(static_cast<uint32_t>(b) / bt.bins_per_owner) : 0;
             const BinPool& pool = bt.pool[owner];
-            uint32_t page = my_open_page[b], fill = my_open_fill[b];
+            uint32_t page = s_open_page[b], fill = s_open_fill[b];
             auto alloc = [&]() -> uint32_t {
                 uint32_t pg = atomicAdd(pool.next_page, 1u);            // (a remote atomic when the pool is a peer's)
                 if (pg >= pool.pool_pages) { *pool.overflow = 1u; pg = pool.pool_pages - 1; }
@@ -163,19 +169,20 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
             };
             if (page == kNoPage || fill == kBinPageEntries) { page = alloc(); fill = 0; }
             const uint32_t len_a = min(cnt, kBinPageEntries - fill);
-            s_seg_a[b] = page * kBinPageEntries + fill;
-            s_len_a[b] = len_a;
+            const uint32_t seg_a = page * kBinPageEntries + fill;
+            uint32_t seg_b = 0;
             s_pool[b] = static_cast<uint32_t>(owner);
             pool.page_fill[page] = fill + len_a;
             fill += len_a;
             if (cnt > len_a) {
                 page = alloc();
                 fill = cnt - len_a;
-                s_seg_b[b] = page * kBinPageEntries;
+                seg_b = page * kBinPageEntries;
                 pool.page_fill[page] = fill;
             }
-            my_open_page[b] = page;
-            my_open_fill[b] = fill;
+            s_tab[b] = make_uint4(s_prefix[b], len_a, seg_a, seg_b - len_a);
+            s_open_page[b] = page;
+            s_open_fill[b] = fill;
         }
         __syncthreads();
 
@@ -184,10 +191,11 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
         for (int k = 0; k < kBinPts; ++k) {
             if (key[k] == 0xffffffffu) continue;
             const uint32_t bin = key[k] >> 13, rank = key[k] & 8191u;
-            const uint32_t at = s_prefix[bin] + rank;
-            st_pos[at] = rank < s_len_a[bin] ? s_seg_a[bin] + rank : s_seg_b[bin] + (rank - s_len_a[bin]);
+            const uint4 tb = s_tab[bin];
+            const uint32_t at = tb.x + rank;
+            st_pos[at] = (rank < tb.y ? tb.z : tb.w) + rank;
             st_cell[at] = cell[k];
-            st_pool[at] = static_cast<uint8_t>(s_pool[bin]);
+            if (multi_pool) st_pool[at] = static_cast<uint8_t>(s_pool[bin]);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) st_val[c * kBinChunk + at] = val[k][c];
         }
@@ -195,7 +203,7 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
 
         // ---- copy out: consecutive threads = consecutive entries of one run = consecutive addresses ----
         for (uint32_t t = tid; t < total; t += kBinThreads) {
-            const BinPool& pool = bt.pool[st_pool[t]];
+            const BinPool& pool = bt.pool[multi_pool ? st_pool[t] : 0];
             const uint32_t at = st_pos[t];
             pool.ent_cell[at] = st_cell[t];
 #pragma unroll
@@ -203,6 +211,7 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
         }
         __syncthreads();
     }
+    for (int b = tid; b < nbins; b += kBinThreads) { my_open_page[b] = s_open_page[b]; my_open_fill[b] = s_open_fill[b]; }
     if (!multi_tile) {
         if (__any_sync(0xffffffffu, any_valid) && (tid & 31) == 0 && touched[0] == 0) touched[0] = 1;
     }
@@ -242,8 +251,9 @@ __global__ void k_bin_page_order(const __grid_constant__ BinPool pool, const uin
 
 // CTA per page, pages in bin order: at any time the resident CTAs work on neighbouring bins, whose
 // records stay in L2.  Same reductions per entry as k_point_direct (update_record).
+constexpr int kAccThreads = 256;
 template <int NADD, int NMAX, int NMIN, int NCH>
-__global__ void __launch_bounds__(kBinThreads)
+__global__ void __launch_bounds__(kAccThreads)
 k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restrict__ order,
                  uint32_t* __restrict__ state, size_t cell_base, const __grid_constant__ PassLayout L)
 {
@@ -263,7 +273,7 @@ k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restric
         const uint32_t cnt = min(pool.page_fill[page], kBinPageEntries);
         const uint32_t e0 = page * kBinPageEntries;
 #pragma unroll 4
-        for (uint32_t t = threadIdx.x; t < cnt; t += kBinThreads) {
+        for (uint32_t t = threadIdx.x; t < cnt; t += kAccThreads) {
             const uint32_t cell = __ldcs(pool.ent_cell + e0 + t);
             float v[kMaxChan] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -293,9 +303,9 @@ cudaError_t acc_nch(cudaStream_t s, unsigned grid, const BinPool& pool, const ui
                     size_t cell_base, const PassLayout& L)
 {
     switch (L.n_chan) {
-    case 0: k_bin_accumulate<NADD, NMAX, NMIN, 0><<<grid, kBinThreads, 0, s>>>(pool, order, state, cell_base, L); break;
-    case 1: k_bin_accumulate<NADD, NMAX, NMIN, 1><<<grid, kBinThreads, 0, s>>>(pool, order, state, cell_base, L); break;
-    case 2: k_bin_accumulate<NADD, NMAX, NMIN, 2><<<grid, kBinThreads, 0, s>>>(pool, order, state, cell_base, L); break;
+    case 0: k_bin_accumulate<NADD, NMAX, NMIN, 0><<<grid, kAccThreads, 0, s>>>(pool, order, state, cell_base, L); break;
+    case 1: k_bin_accumulate<NADD, NMAX, NMIN, 1><<<grid, kAccThreads, 0, s>>>(pool, order, state, cell_base, L); break;
+    case 2: k_bin_accumulate<NADD, NMAX, NMIN, 2><<<grid, kAccThreads, 0, s>>>(pool, order, state, cell_base, L); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -332,12 +342,14 @@ bool bin_supported(const PassLayout& L) { return L.n_chan <= kBinMaxChan; }
 
 size_t bin_scatter_smem(int nbins, int n_chan)
 {
-    return static_cast<size_t>(6 * nbins + 8) * 4 + static_cast<size_t>(kBinChunk) * (8 + 4 * n_chan + 1);
+    const size_t nb4 = (2 * static_cast<size_t>(nbins) + 3) & ~size_t(3);
+    return (nb4 + 4 * static_cast<size_t>(nbins) + 3 * static_cast<size_t>(nbins) + 32) * 4 +
+           static_cast<size_t>(kBinChunk) * (8 + 4 * n_chan + 1);
 }
 
 unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan)
 {
-    // CTAs per SM by shared memory (227 KB usable), at most 2 (<= 106 registers x 256 threads)
+    // CTAs per SM by shared memory (227 KB usable), at most 2 (64 registers x 512 threads each)
     const size_t per = bin_scatter_smem(nbins, n_chan);
     const unsigned by_smem = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / per)));
     return static_cast<unsigned>(sm_count) * by_smem;
