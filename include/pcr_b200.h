@@ -105,7 +105,12 @@ typedef struct pcr_pipeline_desc {
     int32_t                   gpu_fallback_to_cpu;  /* never honoured: no device => CudaError */
     int32_t                   cuda_device_id;
     /* --- additive knobs --- */
-    int32_t                   deterministic;        /* 1 = sort-then-segmented-reduce, bit-reproducible */
+    int32_t                   deterministic;        /* 1 = sort by cell + in-order segmented reduce: bit-reproducible
+                                                       run to run for a fixed chunking and sharding (Point glyph,
+                                                       Gaussian gather); 2 = exact fixed-point accumulation of every
+                                                       float contribution, rounded once at finalize: bit-identical
+                                                       whatever the point order, the ingest chunking and the number
+                                                       of GPUs (all glyphs; ranks combine by integer all-reduce) */
     int32_t                   ring_depth;           /* host-ingest staging slots, 0 = default (3) */
     uint64_t                  ring_slot_points;     /* points per ring chunk, 0 = default (256 Ki staged
                                                        from pageable memory, 2 Mi direct from pinned) */

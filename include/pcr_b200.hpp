@@ -492,7 +492,7 @@ struct PipelineConfig {
     bool        write_cog = false;
 
     // Additive knobs of the B200 path (pcr_pipeline_desc, pcr_b200.h).
-    bool     deterministic = false;
+    int      deterministic = 0;         // 0 off, 1 sort + in-order reduce, 2 exact fixed-point (order/sharding independent)
     int      ring_depth = 0;
     uint64_t ring_slot_points = 0;
     int      staging_threads = 0;
@@ -556,7 +556,7 @@ public:
         d.exec_mode = static_cast<int32_t>(c.exec_mode);
         d.gpu_fallback_to_cpu = c.gpu_fallback_to_cpu ? 1 : 0;
         d.cuda_device_id = c.cuda_device_id;
-        d.deterministic = c.deterministic ? 1 : 0;
+        d.deterministic = c.deterministic;
         d.ring_depth = c.ring_depth;
         d.ring_slot_points = c.ring_slot_points;
         d.staging_threads = c.staging_threads;

@@ -80,6 +80,8 @@ Status Engine::save_state(const std::string& dir)
     CU_TRY(cudaSetDevice(device_));
     // N>1: a rank's records are only its own contribution since the last finalize, and the merged state
     // lives in row slices spread over the ranks; the reference's per-tile files cannot express either.
+    if (exact_)
+        return Status::error(PCR_NOT_IMPLEMENTED, "pipeline: save_state is not available in deterministic mode 2 (exact fixed-point state)");
     if (world_ > 1)
         return Status::error(PCR_NOT_IMPLEMENTED,
                              "pipeline: save_state is not available on a multi-GPU pipeline (the accumulated state "
@@ -142,8 +144,9 @@ Status Engine::load_state(const std::string& dir)
     // N>1: the files are ONE contribution to the merged state; rank 0 takes them into its partial state
     // (merged into the owners' slices at the next finalize), the other ranks keep the identity — loading
     // them everywhere would count the checkpoint world-size times.
-    if (partition_)
-        return Status::error(PCR_NOT_IMPLEMENTED, "pipeline: load_state is not available with the tile-partitioned multi-GPU layout");
+    if (partition_ || exact_)
+        return Status::error(PCR_NOT_IMPLEMENTED, "pipeline: load_state is not available with the tile-partitioned multi-GPU layout "
+                                                  "or in deterministic mode 2");
     if (world_ > 1 && rank_ != 0) return Status::success();
     std::vector<uint32_t> touched(std::max(1, n_tiles_));
     CU_TRY(cudaMemcpy(touched.data(), d_touched_, touched.size() * 4, cudaMemcpyDeviceToHost));

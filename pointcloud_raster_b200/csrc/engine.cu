@@ -333,7 +333,10 @@ Status Engine::init(const pcr_pipeline_desc& d)
     grid_ = d.grid;
     exec_mode_ = d.exec_mode;
     device_ = d.cuda_device_id;
-    deterministic_ = d.deterministic != 0;
+    deterministic_ = d.deterministic == 1;
+    exact_ = d.deterministic == 2;
+    if (d.deterministic < 0 || d.deterministic > 2)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: deterministic must be 0, 1 or 2");
     async_device_ingest_ = d.async_ingest != 0;
     point_variant_ = d.point_kernel == 2 ? POINT_TMA : d.point_kernel == 1 ? POINT_DIRECT : POINT_DIRECT;
     point_kernel_knob_ = d.point_kernel;
@@ -471,6 +474,7 @@ Status Engine::init(const pcr_pipeline_desc& d)
 Status Engine::alloc_state()
 {
     for (Pass& p : passes_) {
+        if (exact_) { ST_TRY(alloc_exact(p)); continue; }          // mode 2 keeps no float records at all
         CU_TRY(cudaMalloc(&p.d_delta[0], cells_ * p.layout.width * sizeof(uint32_t)));
         p.d_state = p.d_delta[0];
     }
@@ -494,6 +498,7 @@ Status Engine::init_state()
 {
     prof_begin(PROF_INIT, compute_);
     for (Pass& p : passes_) {
+        if (exact_) { CU_TRY(launch_exact_init(compute_, p.xa, p.layout)); ++launches_; continue; }
         const size_t n_rec = partition_ ? p.bin.cell1 - p.bin.cell0 : cells_;   // partitioned: my bins' cells only
         for (uint32_t* d : p.d_delta)
             if (d) { CU_TRY(launch_init_state(compute_, d, n_rec, p.layout)); ++launches_; }
@@ -575,7 +580,11 @@ Engine::~Engine()
     }
     peer_unmap();
     if (comm_) engine_comm_destroy(nccl_, comm_);
-    for (Pass& p : passes_) { cudaFree(p.d_delta[0]); cudaFree(p.d_delta[1]); cudaFree(p.d_owned); cudaFree(p.d_combined); bin_free(p); }
+    for (Pass& p : passes_) {
+        cudaFree(p.d_delta[0]); cudaFree(p.d_delta[1]); cudaFree(p.d_owned); cudaFree(p.d_combined); bin_free(p);
+        cudaFree(p.xa.limbs); cudaFree(p.xa.flags); cudaFree(p.xa.ext);
+        cudaFree(p.xa_sum.limbs); cudaFree(p.xa_sum.flags); cudaFree(p.xa_sum.ext);
+    }
     if (h_overflow_) cudaFreeHost(h_overflow_);
     cudaFree(d_touched_buf_[0]);
     cudaFree(d_touched_buf_[1]);
@@ -808,6 +817,7 @@ Status Engine::ingest(const double* x, const double* y, size_t n, const pcr_chan
 bool Engine::use_gather(const Pass& p) const
 {
     if (p.glyph.type != PCR_GLYPH_GAUSSIAN || !gauss_gather_supported(p.layout)) return false;
+    if (exact_) return false;          // mode 2: the scatter kernel's per-cell contributions are summed exactly
     if (gaussian_variant_ == 1) return false;
     if (gaussian_variant_ == 2) return true;
     // auto: the gather needs footprints wide enough to amortise its per-(point,tile) tables.  Measured
@@ -874,6 +884,7 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
 {
     const uint8_t* mask = nullptr;
     ST_TRY(build_mask(n, cp, &mask));
+    if (exact_) return run_passes_exact(dx, dy, n, cp, mask);
     if (deterministic_) ST_TRY(run_passes_deterministic(dx, dy, n, cp, mask));
     // tile-binned Point passes only append entries now; their reductions run bin by bin at finalize
     bool any_binned = false;
@@ -1154,6 +1165,11 @@ Status Engine::finalize_single()
         if (reductions_[i].rejected)   // never accumulated: all NaN (0xFFFFFFFF is a NaN)
             CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), compute_));
     for (Pass& p : passes_) {
+        if (exact_) {
+            CU_TRY(launch_finalize_exact(compute_, p.xa, 0, cells_, d_out_, cells_, gp_, p.layout, p.fin, d_touched_));
+            ++launches_;
+            continue;
+        }
         StateParts parts{};
         parts.part[0] = p.d_state;
         parts.n = 1;

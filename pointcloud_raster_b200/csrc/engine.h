@@ -24,6 +24,7 @@
 #include "../../include/pcr_b200.h"
 #include "kernels.cuh"
 #include "bin_kernels.cuh"
+#include "exact_acc.cuh"
 
 namespace pcrb {
 
@@ -92,6 +93,8 @@ struct Pass {
     uint32_t* d_delta[2] = {nullptr, nullptr};
     uint32_t* d_owned = nullptr;         // my row slice, accumulated over all finalizes so far
     BinState bin;
+    // deterministic mode 2: exact fixed-point state (exact_acc.cuh); xa_sum = all ranks' states added up
+    XAcc xa{}, xa_sum{};
 };
 
 // Worker pool for the pageable -> pinned staging copies of one host ingest.
@@ -208,6 +211,10 @@ private:
     Status finalize_multi();
     Status finalize_multi_nccl();
     Status finalize_multi_peer();
+    Status finalize_multi_exact();
+    Status alloc_exact(Pass& p);
+    Status run_passes_exact(const double* dx, const double* dy, size_t n, const std::vector<const float*>& cp,
+                            const uint8_t* mask);
     Status peer_map();               // exchange CUDA IPC handles, map every rank's buffers
     void peer_unmap();
     void peer_close_handles();
@@ -232,7 +239,8 @@ private:
     int exec_mode_ = PCR_EXEC_AUTO;
     int device_ = 0;
     int sm_count_ = 148;
-    bool deterministic_ = false;
+    bool deterministic_ = false;     // mode 1: sort by cell, in-order segmented reduce (bit-reproducible run to run)
+    bool exact_ = false;             // mode 2: exact fixed-point accumulation (independent of order, chunking, sharding)
     bool async_device_ingest_ = false;
     int point_variant_ = POINT_DIRECT;
     int point_kernel_knob_ = 0;       // pcr_pipeline_desc::point_kernel as given (3 = force the binned path)

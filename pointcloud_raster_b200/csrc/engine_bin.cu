@@ -26,7 +26,7 @@ Status Engine::bin_setup(Pass& p)
 {
     BinState& b = p.bin;
     b.on = false;
-    if (p.glyph.type != PCR_GLYPH_POINT || deterministic_ || !bin_supported(p.layout)) return Status::success();
+    if (p.glyph.type != PCR_GLYPH_POINT || deterministic_ || exact_ || !bin_supported(p.layout)) return Status::success();
     const size_t W = p.layout.width;
     const size_t state_bytes = cells_ * W * 4;
     const bool forced = point_kernel_knob_ == 3;

@@ -173,6 +173,18 @@ Status Engine::comm_init(const void* id128, int rank, int world)
     world_ = world;
     if (staging_auto_ && !pool_) staging_threads_ = default_staging_threads(world);   // ranks share one host
     CU_TRY(cudaMalloc(&d_touched_all_, std::max(1, n_tiles_) * sizeof(uint32_t)));
+    if (exact_) {            // mode 2 combines with integer all-reduces (any order gives the same bits): no peer mapping
+        for (Pass& p : passes_) {
+            p.xa_sum = p.xa;
+            p.xa_sum.limbs = nullptr; p.xa_sum.flags = nullptr; p.xa_sum.ext = nullptr;
+            if (p.layout.n_add) {
+                CU_TRY(cudaMalloc(&p.xa_sum.limbs, xacc_limb_bytes(cells_, p.layout)));
+                CU_TRY(cudaMalloc(&p.xa_sum.flags, xacc_flag_bytes(cells_, p.layout)));
+            }
+            if (p.layout.n_max + p.layout.n_min) CU_TRY(cudaMalloc(&p.xa_sum.ext, xacc_ext_bytes(cells_, p.layout)));
+        }
+        return Status::success();
+    }
     if (comm_mode_ != 1) {
         Status s = peer_map();
         if (!s.ok() && (comm_mode_ == 2 || comm_layout_ == 2)) return s;     // peer memory was demanded
@@ -571,8 +583,85 @@ Status Engine::peer_quiesce()
     return Status::success();
 }
 
+// Deterministic mode 2 on N ranks: the exact states are integers, so ANY reduction order gives the same
+// bits — NCCL's all-reduce (ring, tree or NVLS in-switch) is used as it is: sum over the int64 limbs, max
+// over the flag bytes and the max words, min over the min words.  Every rank then finalizes the whole grid.
+Status Engine::finalize_multi_exact()
+{
+    constexpr int kInt32 = 2, kInt64 = 4, kMin = 3;
+    const size_t nt = std::max(1, n_tiles_);
+    NC_TRY(nccl_->AllReduce(d_touched_, d_touched_all_, nt, NcclApi::kUint32, NcclApi::kMax, comm_, compute_));
+    prof_begin(PROF_PUSH, compute_);
+    for (Pass& p : passes_) {
+        const PassLayout& L = p.layout;
+        if (L.n_add) {
+            NC_TRY(nccl_->AllReduce(p.xa.limbs, p.xa_sum.limbs, cells_ * L.n_add * kXLimbs, kInt64, NcclApi::kSum, comm_, compute_));
+            NC_TRY(nccl_->AllReduce(p.xa.flags, p.xa_sum.flags, xacc_flag_bytes(cells_, L), NcclApi::kUint8, NcclApi::kMax, comm_, compute_));
+        }
+        if (L.n_max) NC_TRY(nccl_->AllReduce(p.xa.ext, p.xa_sum.ext, cells_ * L.n_max, kInt32, NcclApi::kMax, comm_, compute_));
+        if (L.n_min) NC_TRY(nccl_->AllReduce(p.xa.ext + cells_ * L.n_max, p.xa_sum.ext + cells_ * L.n_max, cells_ * L.n_min, kInt32, kMin, comm_, compute_));
+    }
+    prof_end(compute_);
+    prof_begin(PROF_FIN, compute_);
+    for (size_t i = 0; i < reductions_.size(); ++i)
+        if (reductions_[i].rejected)
+            CU_TRY(cudaMemsetAsync(d_out_ + i * cells_, 0xFF, cells_ * sizeof(float), compute_));
+    for (Pass& p : passes_) {
+        CU_TRY(launch_finalize_exact(compute_, p.xa_sum, 0, cells_, d_out_, cells_, gp_, p.layout, p.fin, d_touched_all_));
+        ++launches_;
+    }
+    prof_end(compute_);
+    return Status::success();
+}
+
+Status Engine::alloc_exact(Pass& p)
+{
+    p.xa.cells = cells_;
+    const PassLayout& L = p.layout;
+    if (L.n_add) {
+        CU_TRY(cudaMalloc(&p.xa.limbs, xacc_limb_bytes(cells_, L)));
+        CU_TRY(cudaMalloc(&p.xa.flags, xacc_flag_bytes(cells_, L)));
+    }
+    if (L.n_max + L.n_min) CU_TRY(cudaMalloc(&p.xa.ext, xacc_ext_bytes(cells_, L)));
+    return Status::success();
+}
+
+Status Engine::run_passes_exact(const double* dx, const double* dy, size_t n, const std::vector<const float*>& cp,
+                                const uint8_t* mask)
+{
+    prof_begin(PROF_ACC, compute_);
+    for (Pass& p : passes_) {
+        ChannelPtrs ch{};
+        for (size_t c = 0; c < p.channels.size(); ++c) ch.p[c] = cp[channel_slot(p.channels[c])];
+        if (p.glyph.type == PCR_GLYPH_POINT) {
+            CU_TRY(launch_point_exact(compute_, mask, dx, dy, ch, n, p.xa, gp_, p.layout, d_touched_));
+        } else {
+            GlyphParams g{};
+            auto opt = [&](const std::string& name) -> const float* {
+                const int s = name.empty() ? -1 : channel_slot(name);
+                return s < 0 ? nullptr : cp[s];
+            };
+            g.direction = opt(p.glyph.direction_channel);     g.default_direction = p.glyph.default_direction;
+            g.half_length = opt(p.glyph.half_length_channel); g.default_half_length = p.glyph.default_half_length;
+            g.sigma_x = opt(p.glyph.sigma_x_channel);         g.default_sigma_x = p.glyph.default_sigma_x;
+            g.sigma_y = opt(p.glyph.sigma_y_channel);         g.default_sigma_y = p.glyph.default_sigma_y;
+            g.rotation = opt(p.glyph.rotation_channel);       g.default_rotation = p.glyph.default_rotation;
+            g.max_radius_cells = p.glyph.max_radius_cells;
+            if (p.glyph.type == PCR_GLYPH_LINE)
+                CU_TRY(launch_line_accumulate(compute_, mask, dx, dy, ch, g, n, nullptr, gp_, p.layout, d_touched_, &p.xa));
+            else
+                CU_TRY(launch_gaussian_accumulate(compute_, mask, dx, dy, ch, g, n, nullptr, gp_, p.layout, d_touched_, &p.xa));
+        }
+        ++launches_;
+    }
+    prof_end(compute_);
+    prof_points_ += n;
+    return Status::success();
+}
+
 Status Engine::finalize_multi()
 {
+    if (exact_) return finalize_multi_exact();
     if (partition_) return finalize_multi_part();
     return peer_ok_ ? finalize_multi_peer() : finalize_multi_nccl();
 }

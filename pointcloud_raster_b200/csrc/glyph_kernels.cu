@@ -12,6 +12,7 @@
 // [ sum(v_c * w) for each distinct value channel c ..., sum(w) ] and go out as one
 // vector red per painted cell.
 #include "kernels.cuh"
+#include "exact_acc.cuh"
 
 namespace pcrb {
 
@@ -43,10 +44,10 @@ __device__ __forceinline__ ClipRect clip_of(const GridParams& g, int col, int ro
     return t;
 }
 
-template <int NADD>
+template <int NADD, bool XACC = false>
 __device__ __forceinline__ void paint(uint32_t* __restrict__ state, const GridParams& g, int cx,
                                       int cy, const PassLayout& L, const float (&v)[kMaxChan],
-                                      float w)
+                                      float w, const XAcc* xa = nullptr)
 {
     constexpr int W = NADD <= 1 ? 1 : NADD <= 2 ? 2 : 4;
     float a[kMaxAdd];
@@ -60,8 +61,13 @@ __device__ __forceinline__ void paint(uint32_t* __restrict__ state, const GridPa
             a[j] = 0.0f;
         }
     }
-    float* rec = reinterpret_cast<float*>(state) + (static_cast<size_t>(cy) * g.width + cx) * W;
-    red_add_words<NADD>(rec, a);
+    if constexpr (XACC) {                          // deterministic mode 2: exact, order-independent
+#pragma unroll
+        for (int j = 0; j < NADD; ++j) xacc_add(*xa, j, static_cast<size_t>(cy) * g.width + cx, a[j]);
+    } else {
+        float* rec = reinterpret_cast<float*>(state) + (static_cast<size_t>(cy) * g.width + cx) * W;
+        red_add_words<NADD>(rec, a);
+    }
 }
 
 __device__ __forceinline__ void mark_touched(const GridParams& g, uint32_t* touched, int col, int row)
@@ -73,12 +79,12 @@ __device__ __forceinline__ void mark_touched(const GridParams& g, uint32_t* touc
 // ---------------------------------------------------------------------------
 // Line: one thread per point, Bresenham walk.
 // ---------------------------------------------------------------------------
-template <int NADD>
+template <int NADD, bool XACC>
 __global__ void __launch_bounds__(kThreads)
 k_line(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
        const __grid_constant__ ChannelPtrs ch, const __grid_constant__ GlyphParams gp, size_t n,
        uint32_t* __restrict__ state, const __grid_constant__ GridParams g,
-       const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched)
+       const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched, const __grid_constant__ XAcc xa)
 {
     const size_t p = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
     if (p >= n || (mask != nullptr && mask[p] == 0)) return;
@@ -114,7 +120,7 @@ k_line(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const do
     const int max_steps = 2 * (adx + ady) + 2;
     for (int s = 0; s <= max_steps; ++s) {
         if (cx >= clip.c0 && cx < clip.c1 && cy >= clip.r0 && cy < clip.r1)
-            paint<NADD>(state, g, cx, cy, L, v, 1.0f);
+            paint<NADD, XACC>(state, g, cx, cy, L, v, 1.0f, &xa);
         if (cx == ix1 && cy == iy1) break;
         const int e2 = 2 * err;
         if (e2 > -ady) { err -= ady; cx += stepx; }
@@ -126,12 +132,12 @@ k_line(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const do
 // Gaussian: one warp per point, lanes sweep the (2r+1)^2 footprint row-major so
 // the reds of a warp land on consecutive records.
 // ---------------------------------------------------------------------------
-template <int NADD>
+template <int NADD, bool XACC>
 __global__ void __launch_bounds__(kThreads)
 k_gaussian_warp(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
                 const __grid_constant__ ChannelPtrs ch, const __grid_constant__ GlyphParams gp,
                 size_t n, uint32_t* __restrict__ state, const __grid_constant__ GridParams g,
-                const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched)
+                const __grid_constant__ PassLayout L, uint32_t* __restrict__ touched, const __grid_constant__ XAcc xa)
 {
     __shared__ float s_profile[kThreads / 32][2][kMaxProfile];     // per warp: wx[], wy[]
     const int lane = threadIdx.x & 31;
@@ -208,7 +214,7 @@ k_gaussian_warp(const uint8_t* __restrict__ mask, const double* __restrict__ xs,
                 const int gc = icx + dx, gr = icy + dy;
                 if (gc >= clip.c0 && gc < clip.c1 && gr >= clip.r0 && gr < clip.r1) {
                     const float w = __fmul_rn(wxs[dx + r], wys[dy + r]);
-                    if (!(w < 1e-6f)) paint<NADD>(state, g, gc, gr, L, v, w);
+                    if (!(w < 1e-6f)) paint<NADD, XACC>(state, g, gc, gr, L, v, w, &xa);
                 }
                 dx += 32;
                 while (dx > r) { dx -= side; ++dy; }
@@ -228,7 +234,7 @@ k_gaussian_warp(const uint8_t* __restrict__ mask, const double* __restrict__ xs,
                 const float qx = __fdiv_rn(rx, sx), qy = __fdiv_rn(ry, sy);
                 const float e = __fmul_rn(-0.5f, __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)));
                 const float w = expf(e);
-                if (!(w < 1e-6f)) paint<NADD>(state, g, gc, gr, L, v, w);
+                if (!(w < 1e-6f)) paint<NADD, XACC>(state, g, gc, gr, L, v, w, &xa);
             }
             dx += 32;
             while (dx > r) { dx -= side; ++dy; }
@@ -253,12 +259,13 @@ cudaError_t dispatch_nadd(int n_add, F&& f)
 cudaError_t launch_line_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                    const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                    uint32_t* state, const GridParams& g, const PassLayout& L,
-                                   uint32_t* touched)
+                                   uint32_t* touched, const XAcc* exact)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>((n + kThreads - 1) / kThreads);
     return dispatch_nadd(L.n_add, [&](auto na) {
-        k_line<decltype(na)::value><<<grid, kThreads, 0, s>>>(mask, x, y, ch, gp, n, state, g, L, touched);
+        if (exact) k_line<decltype(na)::value, true><<<grid, kThreads, 0, s>>>(mask, x, y, ch, gp, n, state, g, L, touched, *exact);
+        else k_line<decltype(na)::value, false><<<grid, kThreads, 0, s>>>(mask, x, y, ch, gp, n, state, g, L, touched, XAcc{});
         return cudaGetLastError();
     });
 }
@@ -266,15 +273,19 @@ cudaError_t launch_line_accumulate(cudaStream_t s, const uint8_t* mask, const do
 cudaError_t launch_gaussian_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                        const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                        uint32_t* state, const GridParams& g, const PassLayout& L,
-                                       uint32_t* touched)
+                                       uint32_t* touched, const XAcc* exact)
 {
     if (n == 0) return cudaSuccess;
     const size_t warps_per_block = kThreads / 32;
     size_t blocks = (n + warps_per_block - 1) / warps_per_block;
     if (blocks > 148 * 64) blocks = 148 * 64;
     return dispatch_nadd(L.n_add, [&](auto na) {
-        k_gaussian_warp<decltype(na)::value><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(
-            mask, x, y, ch, gp, n, state, g, L, touched);
+        if (exact)
+            k_gaussian_warp<decltype(na)::value, true><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(
+                mask, x, y, ch, gp, n, state, g, L, touched, *exact);
+        else
+            k_gaussian_warp<decltype(na)::value, false><<<static_cast<unsigned>(blocks), kThreads, 0, s>>>(
+                mask, x, y, ch, gp, n, state, g, L, touched, XAcc{});
         return cudaGetLastError();
     });
 }

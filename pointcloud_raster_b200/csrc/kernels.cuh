@@ -60,17 +60,32 @@ cudaError_t launch_point_accumulate(cudaStream_t s, int variant, bool warp_aggre
                                     size_t n, uint32_t* state, const GridParams& g,
                                     const PassLayout& L, uint32_t* touched, int sm_count);
 
-// Line glyph (accumulate_glyph_line_cpu, src/engine/glyph_kernels.cu:188-281)
+// Line glyph (accumulate_glyph_line_cpu, src/engine/glyph_kernels.cu:188-281).
+// `exact` (may be null): deterministic mode 2 — contributions go into the exact fixed-point state of
+// exact_acc.cuh instead of float reductions on `state`.
+struct XAcc;
 cudaError_t launch_line_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                    const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                    uint32_t* state, const GridParams& g, const PassLayout& L,
-                                   uint32_t* touched);
+                                   uint32_t* touched, const XAcc* exact = nullptr);
 
 // Gaussian glyph (accumulate_glyph_gaussian_cpu, src/engine/glyph_kernels.cu:79-183)
 cudaError_t launch_gaussian_accumulate(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                        const ChannelPtrs& ch, const GlyphParams& gp, size_t n,
                                        uint32_t* state, const GridParams& g, const PassLayout& L,
-                                       uint32_t* touched);
+                                       uint32_t* touched, const XAcc* exact = nullptr);
+
+// deterministic mode 2 (exact_kernels.cu)
+size_t xacc_limb_bytes(size_t cells, const PassLayout& L);
+size_t xacc_flag_bytes(size_t cells, const PassLayout& L);
+size_t xacc_ext_bytes(size_t cells, const PassLayout& L);
+cudaError_t launch_exact_init(cudaStream_t s, const XAcc& xa, const PassLayout& L);
+cudaError_t launch_point_exact(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
+                               const ChannelPtrs& ch, size_t n, const XAcc& xa, const GridParams& g,
+                               const PassLayout& L, uint32_t* touched);
+cudaError_t launch_finalize_exact(cudaStream_t s, const XAcc& xa, size_t cell0, size_t count, float* out,
+                                  size_t band_stride, const GridParams& g, const PassLayout& L,
+                                  const FinalizeProgram& fp, const uint32_t* touched);
 
 // merge (Op::merge over parts) + finalize (Op::finalize) + touched-tile NaN rule,
 // for cells [cell0, cell0+count); writes out[band*band_stride + cell].

@@ -768,7 +768,7 @@ class Pipeline:
         desc.exec_mode = int(cfg.exec_mode)
         desc.gpu_fallback_to_cpu = int(bool(cfg.gpu_fallback_to_cpu))
         desc.cuda_device_id = int(getattr(cfg, "cuda_device_id", 0))
-        desc.deterministic = int(bool(getattr(cfg, "deterministic", False)))
+        desc.deterministic = int(getattr(cfg, "deterministic", 0))      # False/True or 0/1/2
         desc.ring_depth = int(getattr(cfg, "ring_depth", 0))
         desc.ring_slot_points = int(getattr(cfg, "ring_slot_points", 0))
         desc.staging_threads = int(getattr(cfg, "staging_threads", 0))

@@ -313,3 +313,64 @@ def test_multi_gpu_partitioned_grid_point_exchange(gpu_pcr, oracle, root_only):
                 g[int(c0):int(c1)] = b.reshape(-1)[int(c0):int(c1)]
         got = [g.reshape(gc.height, gc.width) for g in got]
         compare_bands(oracle, gd, [(xs, ys, chs)], specs, ref, got, f"partitioned + distributed bands, {world} GPUs")
+
+
+# ---- deterministic mode 2: the same bits on 1 and N GPUs ---------------------------------------------------
+def _exact_worker(rank, world, id_path, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import time
+    from pointcloud_raster_b200 import pcr
+    from util import make_grid, cloud as mk
+    from test_exact_mode_gpu import _glyph_specs, _cloud
+    if rank == 0:
+        open(id_path + ".tmp", "wb").write(pcr.comm_unique_id())
+        os.rename(id_path + ".tmp", id_path)
+    while not os.path.exists(id_path):
+        time.sleep(0.01)
+    uid = open(id_path, "rb").read()
+    w, h = 160, 120
+    gc = make_grid(pcr, w, h, tile=64)
+    x, y, ch = _cloud(60_000, w, h, 5)
+    specs = _glyph_specs(pcr)
+    cfg = pcr.PipelineConfig(); cfg.grid = gc; cfg.reductions = specs; cfg.exec_mode = pcr.ExecutionMode.GPU
+    cfg.cuda_device_id = rank; cfg.deterministic = 2
+    p = pcr.Pipeline.create(cfg)
+    assert p is not None
+    p.comm_init(uid, rank, world)
+    n = len(x)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    half = (lo + 2 * hi) // 3                          # two unequal ingest + finalize rounds
+    for a, b in ((lo, half), (half, hi)):
+        p.ingest(mk(pcr, x[a:b], y[a:b], {k: v[a:b] for k, v in ch.items()}))
+        p.finalize()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), *[np.array(p.result().band_array(i)) for i in range(len(specs))])
+    p.comm_barrier()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_exact_mode_equals_single_gpu_bit_for_bit(gpu_pcr):
+    if gpu_pcr.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import make_grid, run_product
+    from test_exact_mode_gpu import _glyph_specs, _cloud
+    world = min(gpu_pcr.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as d:
+        procs = [ctx.Process(target=_exact_worker, args=(r, world, os.path.join(d, "id"), d)) for r in range(world)]
+        for pr in procs: pr.start()
+        for pr in procs: pr.join(300)
+        assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+        per_rank = []
+        for r in range(world):
+            z = np.load(os.path.join(d, f"rank{r}.npz"))
+            per_rank.append([z[k] for k in sorted(z.files, key=lambda s: int(s.split("_")[1]))])
+    pcr = gpu_pcr
+    w, h = 160, 120
+    gc = make_grid(pcr, w, h, tile=64)
+    x, y, ch = _cloud(60_000, w, h, 5)
+    single, _ = run_product(pcr, gc, [(x, y, ch)], _glyph_specs(pcr), deterministic=2)
+    for r in range(world):
+        for i, (a, b) in enumerate(zip(single, per_rank[r])):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"rank {r} band {i}: {world}-GPU bits differ from 1 GPU"

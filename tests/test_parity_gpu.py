@@ -443,6 +443,37 @@ def test_full_size_gaussian_config(gpu_pcr, sigma):
         assert np.array_equal(a, b, equal_nan=True)
 
 
+# BASELINE config 4 against the ORACLE (not kernel against kernel): the first 200k points of the config-4 cloud,
+# per-point sigma channel 4 / 16, max_radius_cells 32 (625 / 4225 cells per point), on the full 1000 x 1000
+# grid, through both Gaussian kernels.  The C oracle needs ~5 ns per painted cell, which bounds the subsample.
+@pytest.mark.parametrize("sigma", [4.0, 16.0])
+def test_config4_subsample_vs_oracle(gpu_pcr, oracle, sigma):
+    gc = make_grid(gpu_pcr, 1000, 1000)
+    x, y, ch = uniform_cloud(5_000_000, 1000, 1000, seed=42)
+    n = 200_000
+    x, y = x[:n], y[:n]
+    ch = {"value": ch["value"][:n], "sigma": np.full(n, sigma, np.float32)}
+    specs = []
+    for t in ("WeightedAverage", "Count"):
+        s = gpu_pcr.gaussian_splat_spec("value", "sigma", "sigma", max_radius_cells=32.0)
+        s.type = getattr(gpu_pcr.ReductionType, t)
+        specs.append(s)
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, [(x, y, ch)], specs)
+
+    class Memo:                                  # the f64 replays behind the tolerances: once per spec, not per kernel
+        def __init__(self, o): self.o, self.c = o, {}
+        def bounds(self, gd_, clouds_, s_, want_weight=False):
+            k = (id(s_), want_weight)
+            if k not in self.c:
+                self.c[k] = self.o.bounds(gd_, clouds_, s_, want_weight=want_weight)
+            return self.c[k]
+    memo = Memo(oracle)
+    for kernel, name in ((1, "scatter"), (2, "gather")):
+        got, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs, gaussian_kernel=kernel)
+        compare_bands(memo, gd, [(x, y, ch)], specs, ref, got, f"config 4 sigma={sigma} {name}", device_weights=True)
+
+
 # ---- BASELINE config 5 at single-GPU scale: 20000 x 20000 grid (25 reference tiles), clustered ----
 def test_config5_like_large_grid(gpu_pcr):
     W = 20000
