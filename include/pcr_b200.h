@@ -139,7 +139,7 @@ typedef struct pcr_pipeline_desc {
     int32_t                   bin_cells_log2;       /* tile binning: a bin = 2^k consecutive cells; 0 = auto
                                                        (the records of one bin <= 64 MB, at most 1024 bins) */
     uint64_t                  bin_pool_points;      /* tile binning: entries the pool holds before it is folded
-                                                       early; 0 = auto (a quarter of the free HBM, <= 2^30) */
+                                                       early; 0 = auto (a quarter of the free HBM, <= 2^31) */
     int32_t                   comm_layout;          /* N>1: 0 = auto, 1 = replicated partial grids merged at finalize,
                                                        2 = tile-partitioned grid: every rank owns a contiguous range
                                                        of bins, points are exchanged (all-to-all over NVLink peer
@@ -257,15 +257,31 @@ int pcr_pipeline_load_state(pcr_pipeline *p, const char *dir);
 /* ---- GeoTIFF out (GDAL-free; host only) --------------------------------------- */
 /* write_geotiff, src/io/grid_io.cpp:39-182 (called by Pipeline::finalize when output_path is set,
  * src/engine/pipeline.cpp:1350-1361): Float32 tiled (Big)TIFF, one plane per band, nodata NaN, band
- * descriptions, geotransform of GridConfig::gdal_geotransform, EPSG GeoKeys.  compress: "NONE" or
- * "DEFLATE".  bands[b] = rows*cols row-major floats (host). */
+ * descriptions, geotransform of GridConfig::gdal_geotransform, EPSG GeoKeys.  compress: "NONE", "LZW" (the
+ * reference's default, include/pcr/io/grid_io.h:18) or "DEFLATE".  cloud_optimized != 0 adds the overview
+ * pyramid of grid_io.cpp:155-176 (levels 2, 4, ... while min(width, height) / level >= 256; NaN-aware AVERAGE).
+ * bands[b] = rows*cols row-major floats (host). */
 int pcr_geotiff_write(const char *path, const float *const *bands, int32_t num_bands,
                       const pcr_grid_desc *grid, const char *const *band_names, int32_t epsg,
                       const char *compress, int32_t compress_level, int32_t tile_width,
-                      int32_t tile_height, int32_t bigtiff);
+                      int32_t tile_height, int32_t bigtiff, int32_t cloud_optimized);
+/* TiledGeoTiffWriter, include/pcr/io/grid_io.h:44-70, src/io/grid_io.cpp:185-380: open, write the finalized
+ * data of one reference tile at a time (band-sequential, tile_cols x tile_rows floats per band, tile geometry =
+ * GridConfig::tile_cell_range of grid->tile_width/height), close (writes the file and its overviews).
+ * Tiles never written stay NaN. */
+int pcr_geotiff_tiled_open(const char *path, const pcr_grid_desc *grid, const char *const *band_names,
+                           int32_t num_bands, int32_t epsg, const char *compress, int32_t compress_level,
+                           int32_t tile_width, int32_t tile_height, int32_t bigtiff, int32_t cloud_optimized,
+                           void **handle);
+int pcr_geotiff_tiled_write_tile(void *handle, int32_t tile_row, int32_t tile_col, const float *data,
+                                 int32_t num_bands);
+int pcr_geotiff_tiled_close(void *handle);
 /* read_geotiff_info, src/io/grid_io.cpp:395-445; bounds = {min_x, min_y, max_x, max_y} */
 int pcr_geotiff_read_info(const char *path, int32_t *width, int32_t *height, int32_t *num_bands,
                           int32_t *epsg, double bounds[4]);
+/* read_geotiff_band, src/io/grid_io.cpp:445-497: one band of the full-resolution image into `data`
+ * (width*height floats); files of this writer's layout (tiled, band-separate, NONE/LZW/DEFLATE). */
+int pcr_geotiff_read_band(const char *path, int32_t band_index, float *data, int32_t width, int32_t height);
 const char *pcr_geotiff_last_error(void);
 
 /* ---- profiling (new; feeds bench.py's roofline block) ---------------------- */

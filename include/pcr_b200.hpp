@@ -383,7 +383,7 @@ private:
 // ---- GeoTIFF (GDAL-free writer in the library) ------------------------------------------
 struct GeoTiffOptions {
     bool        cloud_optimized = false;
-    std::string compress = "LZW";        // NONE and DEFLATE are written as such; others fall back to DEFLATE
+    std::string compress = "LZW";        // NONE, LZW, DEFLATE (ZSTD: NotImplemented)
     int         compress_level = 6;
     int         tile_width = 256, tile_height = 256;
     bool        bigtiff = true;
@@ -403,7 +403,7 @@ inline Status write_geotiff(const std::string& path, const Grid& grid, const Gri
     const pcr_grid_desc d = config.desc();
     const int rc = pcr_geotiff_write(path.c_str(), bands.data(), grid.num_bands(), &d, cnames.data(),
                                      config.crs.epsg, o.compress.c_str(), o.compress_level, o.tile_width,
-                                     o.tile_height, o.bigtiff ? 1 : 0);
+                                     o.tile_height, o.bigtiff ? 1 : 0, o.cloud_optimized ? 1 : 0);
     if (rc == PCR_OK) return Status::success();
     const char* m = pcr_geotiff_last_error();
     return Status::error(static_cast<StatusCode>(rc), m ? m : "GeoTIFF error");
@@ -423,6 +423,61 @@ inline Status read_geotiff_info(const std::string& path, int& width, int& height
     bounds = BBox(b[0], b[1], b[2], b[3]);
     return Status::success();
 }
+
+inline Status read_geotiff_band(const std::string& path, int band_index, float* data, int width, int height)
+{
+    const int rc = pcr_geotiff_read_band(path.c_str(), band_index, data, width, height);
+    if (rc == PCR_OK) return Status::success();
+    const char* m = pcr_geotiff_last_error();
+    return Status::error(static_cast<StatusCode>(rc), m ? m : "GeoTIFF error");
+}
+
+// include/pcr/io/grid_io.h:44-70: tiles arrive one at a time; the file (and its overviews) is written at close()
+class TiledGeoTiffWriter {
+public:
+    ~TiledGeoTiffWriter() { if (h_) pcr_geotiff_tiled_close(h_); }
+    TiledGeoTiffWriter(const TiledGeoTiffWriter&) = delete;
+    TiledGeoTiffWriter& operator=(const TiledGeoTiffWriter&) = delete;
+
+    static std::unique_ptr<TiledGeoTiffWriter> open(const std::string& path, const GridConfig& config,
+                                                    const std::vector<std::string>& band_names,
+                                                    const GeoTiffOptions& o = GeoTiffOptions())
+    {
+        std::vector<const char*> names;
+        for (const auto& n : band_names) names.push_back(n.c_str());
+        const pcr_grid_desc d = config.desc();
+        void* h = nullptr;
+        const int rc = pcr_geotiff_tiled_open(path.c_str(), &d, names.data(), static_cast<int32_t>(names.size()),
+                                              config.crs.epsg, o.compress.c_str(), o.compress_level, o.tile_width,
+                                              o.tile_height, o.bigtiff ? 1 : 0, o.cloud_optimized ? 1 : 0, &h);
+        if (rc != PCR_OK || !h) return nullptr;
+        return std::unique_ptr<TiledGeoTiffWriter>(new TiledGeoTiffWriter(h));
+    }
+
+    Status write_tile(TileIndex tile, const float* data, int num_bands)
+    {
+        if (!h_) return Status::error(StatusCode::InvalidArgument, "writer not open");
+        const int rc = pcr_geotiff_tiled_write_tile(h_, tile.row, tile.col, data, num_bands);
+        if (rc == PCR_OK) return Status::success();
+        const char* m = pcr_geotiff_last_error();
+        return Status::error(static_cast<StatusCode>(rc), m ? m : "GeoTIFF error");
+    }
+
+    Status close()
+    {
+        if (!h_) return Status::error(StatusCode::InvalidArgument, "writer not open");
+        void* h = h_;
+        h_ = nullptr;
+        const int rc = pcr_geotiff_tiled_close(h);
+        if (rc == PCR_OK) return Status::success();
+        const char* m = pcr_geotiff_last_error();
+        return Status::error(static_cast<StatusCode>(rc), m ? m : "GeoTIFF error");
+    }
+
+private:
+    explicit TiledGeoTiffWriter(void* h) : h_(h) {}
+    void* h_ = nullptr;
+};
 
 // ---- specs ----------------------------------------------------------------------------------
 struct FilterPredicate {

@@ -113,7 +113,13 @@ SYMBOLS = [
     ("pcr_pipeline_synchronize", C.c_int, [C.c_void_p]),
     ("pcr_geotiff_write", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(GridDesc),
                                     C.POINTER(C.c_char_p), C.c_int32, C.c_char_p, C.c_int32, C.c_int32,
-                                    C.c_int32, C.c_int32]),
+                                    C.c_int32, C.c_int32, C.c_int32]),
+    ("pcr_geotiff_tiled_open", C.c_int, [C.c_char_p, C.POINTER(GridDesc), C.POINTER(C.c_char_p), C.c_int32, C.c_int32,
+                                         C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_void_p)]),
+    ("pcr_geotiff_tiled_write_tile", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32]),
+    ("pcr_geotiff_tiled_close", C.c_int, [C.c_void_p]),
+    ("pcr_geotiff_read_band", C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_int32]),
     ("pcr_geotiff_read_info", C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     ("pcr_geotiff_last_error", C.c_char_p, []),

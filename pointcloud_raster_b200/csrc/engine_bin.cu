@@ -53,7 +53,7 @@ Status Engine::bin_setup(Pass& p)
     if (want == 0) {
         size_t free_b = 0, total_b = 0;
         CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-        want = std::min<size_t>(size_t(1) << 30, free_b / 4 / entry_bytes);
+        want = std::min<size_t>(size_t(1) << 31, free_b / 4 / entry_bytes);
     }
     want = std::max<size_t>(want, kBinPageEntries);
     const size_t pages = want / kBinPageEntries + chains + 1;

@@ -1050,6 +1050,18 @@ def read_geotiff_info(path):
     return _r(path)
 
 
+def read_geotiff_band(path, band_index, width, height):
+    from .geotiff import read_geotiff_band as _r
+    return _r(path, band_index, width, height)
+
+
+def __getattr__(name):                      # TiledGeoTiffWriter lives in .geotiff (needs the classes above)
+    if name == "TiledGeoTiffWriter":
+        from .geotiff import TiledGeoTiffWriter
+        return TiledGeoTiffWriter
+    raise AttributeError(name)
+
+
 class PointCloudInfo:
     def __init__(self):
         self.num_points = 0
@@ -1120,7 +1132,7 @@ __all__ = [
     'ChannelDesc', 'BandDesc', 'GridConfig', 'Grid', 'PointCloud', 'FilterPredicate', 'FilterSpec',
     'GlyphSpec', 'ReductionSpec', 'PipelineConfig', 'ProgressInfo', 'Pipeline',
     'gaussian_splat_spec', 'line_splat_spec', 'GeoTiffOptions', 'write_geotiff',
-    'read_geotiff_info', 'PointCloudInfo', 'read_point_cloud', 'write_point_cloud',
+    'read_geotiff_info', 'read_geotiff_band', 'TiledGeoTiffWriter', 'PointCloudInfo', 'read_point_cloud', 'write_point_cloud',
     'read_point_cloud_info', 'PointCloudReader',
     'comm_unique_id', 'comm_slice_rows', 'device_count', 'device_name',
 ]
