@@ -37,6 +37,19 @@ constexpr int kBinChunk = kBinThreads * kBinPts;          // 4096 = kBinPageEntr
 static_assert(kBinChunk == static_cast<int>(kBinPageEntries), "a chunk's run must fit two pages");
 constexpr uint32_t kNoPage = 0xffffffffu;
 
+// entry = {cell, values...} as one vector (see BinPool::ent)
+template <int NCH> struct EntryOf;
+template <> struct EntryOf<0> { using type = uint32_t; static constexpr int words = 1; };
+template <> struct EntryOf<1> { using type = uint2;    static constexpr int words = 2; };
+template <> struct EntryOf<2> { using type = uint4;    static constexpr int words = 4; };
+template <int NCH>
+__device__ __forceinline__ typename EntryOf<NCH>::type make_entry(uint32_t cell, const float* v)
+{
+    if constexpr (NCH == 0) return cell;
+    else if constexpr (NCH == 1) return make_uint2(cell, __float_as_uint(v[0]));
+    else return make_uint4(cell, __float_as_uint(v[0]), __float_as_uint(v[1]), 0u);
+}
+
 // Exclusive scan of s_hist[0..nbins) into s_prefix, nbins <= kMaxBins = 4 * kBinThreads.
 __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t* s_hist, uint32_t* s_prefix, int nbins,
                                                     uint32_t* s_warp)
@@ -97,10 +110,10 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
     uint32_t* s_open_page = s_pool + nbins;                               // [nbins]  this CTA's page chains, kept in shared
     uint32_t* s_open_fill = s_open_page + nbins;                          // [nbins]  memory for the life of the launch
     uint32_t* s_warp   = s_open_fill + nbins;                             // [32]
-    uint32_t* st_pos   = s_warp + 32;                                     // [chunk]  destination entry index
-    uint32_t* st_cell  = st_pos + kBinChunk;                              // [chunk]
-    float*    st_val   = reinterpret_cast<float*>(st_cell + kBinChunk);   // [NCH][chunk]
-    uint8_t*  st_pool  = reinterpret_cast<uint8_t*>(st_val + static_cast<size_t>(NCH) * kBinChunk);   // [chunk]
+    using Entry = typename EntryOf<NCH>::type;
+    uint32_t* st_pos   = s_hist + ((nb4 + 7 * nbins + 32 + 3) & ~3);      // [chunk]  destination entry index (16-byte aligned)
+    Entry*    st_ent   = reinterpret_cast<Entry*>(st_pos + kBinChunk);    // [chunk]  {cell, values} in bin order
+    uint8_t*  st_pool  = reinterpret_cast<uint8_t*>(st_ent + kBinChunk);  // [chunk]
 
     const int tid = threadIdx.x;
     uint32_t* my_open_page = bt.open_page + static_cast<size_t>(blockIdx.x) * nbins;
@@ -194,20 +207,15 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
             const uint4 tb = s_tab[bin];
             const uint32_t at = tb.x + rank;
             st_pos[at] = (rank < tb.y ? tb.z : tb.w) + rank;
-            st_cell[at] = cell[k];
+            st_ent[at] = make_entry<NCH>(cell[k], val[k]);
             if (multi_pool) st_pool[at] = static_cast<uint8_t>(s_pool[bin]);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) st_val[c * kBinChunk + at] = val[k][c];
         }
         __syncthreads();
 
         // ---- copy out: consecutive threads = consecutive entries of one run = consecutive addresses ----
         for (uint32_t t = tid; t < total; t += kBinThreads) {
             const BinPool& pool = bt.pool[multi_pool ? st_pool[t] : 0];
-            const uint32_t at = st_pos[t];
-            pool.ent_cell[at] = st_cell[t];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) pool.ent_val[c][at] = st_val[c * kBinChunk + t];
+            reinterpret_cast<Entry*>(pool.ent)[st_pos[t]] = st_ent[t];
         }
         __syncthreads();
     }
@@ -274,10 +282,12 @@ k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restric
         const uint32_t e0 = page * kBinPageEntries;
 #pragma unroll 4
         for (uint32_t t = threadIdx.x; t < cnt; t += kAccThreads) {
-            const uint32_t cell = __ldcs(pool.ent_cell + e0 + t);
+            const auto ent = __ldcs(reinterpret_cast<const typename EntryOf<NCH>::type*>(pool.ent) + e0 + t);
+            uint32_t cell;
             float v[kMaxChan] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) v[c] = __ldcs(pool.ent_val[c] + e0 + t);
+            if constexpr (NCH == 0) cell = ent;
+            else if constexpr (NCH == 1) { cell = ent.x; v[0] = __uint_as_float(ent.y); }
+            else { cell = ent.x; v[0] = __uint_as_float(ent.y); v[1] = __uint_as_float(ent.z); }
             float add[kMaxAdd], mx[kMaxExt], mn[kMaxExt];
 #pragma unroll
             for (int j = 0; j < kMaxAdd; ++j) add[j] = (j < NADD) ? (L.add_src[j] < 0 ? 1.0f : pick(v, L.add_src[j])) : 0.0f;
@@ -343,8 +353,8 @@ bool bin_supported(const PassLayout& L) { return L.n_chan <= kBinMaxChan; }
 size_t bin_scatter_smem(int nbins, int n_chan)
 {
     const size_t nb4 = (2 * static_cast<size_t>(nbins) + 3) & ~size_t(3);
-    return (nb4 + 4 * static_cast<size_t>(nbins) + 3 * static_cast<size_t>(nbins) + 32) * 4 +
-           static_cast<size_t>(kBinChunk) * (8 + 4 * n_chan + 1);
+    return ((nb4 + 7 * static_cast<size_t>(nbins) + 32 + 3) & ~size_t(3)) * 4 +
+           static_cast<size_t>(kBinChunk) * (4 + 4 * bin_entry_words(n_chan) + 1);
 }
 
 unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan)

@@ -8,11 +8,15 @@ namespace pcrb {
 constexpr uint32_t kBinPageEntries = 4096;   // entries per page (= points per scatter chunk)
 constexpr int kMaxBins = 1024;
 constexpr int kBinMaxChan = 2;               // value channels an entry can carry
+inline int bin_entry_words(int n_chan) { return n_chan == 0 ? 1 : n_chan == 1 ? 2 : 4; }
 
 // One rank's entry pool (device pointers; another rank's pool is the same struct over peer memory).
 struct BinPool {
-    uint32_t* ent_cell;                      // [pool_pages * kBinPageEntries] global cell index
-    float*    ent_val[kBinMaxChan];          // [...] channel values, SoA
+    // [pool_pages * kBinPageEntries] entries, array of structures: {cell u32} (no value channel),
+    // {cell u32, value f32} (one channel) or {cell, v0, v1, pad} (two) — one 4 / 8 / 16-byte store per thread, so
+    // a warp's copy-out is one contiguous 128 / 256 / 512-byte write (what the NVLink path wants:
+    // the SoA layout this replaces moved 4-byte stores and ran at 175 GB/s per GPU at N = 8)
+    uint32_t* ent;
     uint32_t* page_bin;                      // [pool_pages] bin a page belongs to
     uint32_t* page_fill;                     // [pool_pages] entries written to a page so far
     uint32_t* next_page;                     // [0] pages handed out so far, [1] overflow flag, [2] cursor of the fold

@@ -48,7 +48,7 @@ Status Engine::bin_setup(Pass& p)
 
     // pool size: every chain ends in one partly filled page, all other pages are full, so T points need at
     // most T / P + chains pages whatever their distribution
-    const size_t entry_bytes = 4 + 4 * static_cast<size_t>(p.layout.n_chan);
+    const size_t entry_bytes = 4 * static_cast<size_t>(bin_entry_words(p.layout.n_chan));
     size_t want = bin_pool_points_;
     if (want == 0) {
         size_t free_b = 0, total_b = 0;
@@ -62,8 +62,7 @@ Status Engine::bin_setup(Pass& p)
     b.pool.pool_pages = static_cast<uint32_t>(pages);
     b.capacity = (pages - chains - 1) * kBinPageEntries;
     const size_t entries = pages * kBinPageEntries;
-    CU_TRY(cudaMalloc(&b.pool.ent_cell, entries * 4));
-    for (int c = 0; c < p.layout.n_chan; ++c) CU_TRY(cudaMalloc(&b.pool.ent_val[c], entries * 4));
+    CU_TRY(cudaMalloc(&b.pool.ent, entries * entry_bytes));
     CU_TRY(cudaMalloc(&b.pool.page_bin, pages * 4));
     CU_TRY(cudaMalloc(&b.pool.page_fill, pages * 4));
     CU_TRY(cudaMalloc(&b.pool.next_page, 4 * sizeof(uint32_t)));
@@ -86,8 +85,7 @@ Status Engine::bin_setup(Pass& p)
 void Engine::bin_free(Pass& p)
 {
     BinState& b = p.bin;
-    cudaFree(b.pool.ent_cell);
-    for (float* v : b.pool.ent_val) cudaFree(v);
+    cudaFree(b.pool.ent);
     cudaFree(b.pool.page_bin); cudaFree(b.pool.page_fill); cudaFree(b.pool.next_page);
     cudaFree(b.bin_pages); cudaFree(b.bin_first); cudaFree(b.order); cudaFree(b.open_page); cudaFree(b.open_fill);
     b = BinState{};

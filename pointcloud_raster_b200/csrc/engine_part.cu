@@ -7,7 +7,7 @@
 //
 //   ingest    k_bin_scatter routes a rank's points and appends each entry {cell, value} to a page in the
 //             pool of the rank that OWNS the entry's bin — local memory for its own bins, NVLink peer
-//             memory (posted 4-byte-coalesced stores, one remote atomic per 4096-entry page) for the others.
+//             memory (posted stores, a warp writes 256 contiguous bytes; one remote atomic per 4096-entry page) for the others.
 //             This is the all-to-all, fused into the binning kernel: 8 B per point and channel cross the
 //             fabric instead of the 20 B of the raw point, and nothing waits for anything.
 //   finalize  every rank announces "my entries have landed" (flag store, system scope), waits for the same
@@ -49,8 +49,7 @@ Status Engine::partition_setup()
     std::vector<void*> mine;
     for (Pass& p : passes_) {
         BinPool& q = p.bin.pool;
-        mine.push_back(q.ent_cell);
-        for (int c = 0; c < kBinMaxChan; ++c) mine.push_back(c < p.layout.n_chan ? static_cast<void*>(q.ent_val[c]) : nullptr);
+        mine.push_back(q.ent);
         mine.push_back(q.page_bin);
         mine.push_back(q.page_fill);
         mine.push_back(q.next_page);
@@ -71,15 +70,14 @@ Status Engine::partition_setup()
             BinPool q = b.pool;                      // same geometry (pool_pages) on every rank: same free-memory rule
             const std::vector<void*>& h = all[k];
             size_t j = at;
-            q.ent_cell = static_cast<uint32_t*>(h[j++]);
-            for (int c = 0; c < kBinMaxChan; ++c) q.ent_val[c] = static_cast<float*>(h[j++]);
+            q.ent = static_cast<uint32_t*>(h[j++]);
             q.page_bin = static_cast<uint32_t*>(h[j++]);
             q.page_fill = static_cast<uint32_t*>(h[j++]);
             q.next_page = static_cast<uint32_t*>(h[j++]);
             q.overflow = q.next_page + 1;
             b.peer_pool[k] = q;
         }
-        at += 4 + kBinMaxChan;
+        at += 4;
         // records: only my cells.  (create() allocated the whole grid before the world size was known.)
         const size_t W = p.layout.width;
         CU_TRY(cudaStreamSynchronize(compute_));
