@@ -42,6 +42,20 @@ template <int NCH> struct EntryOf;
 template <> struct EntryOf<0> { using type = uint32_t; static constexpr int words = 1; };
 template <> struct EntryOf<1> { using type = uint2;    static constexpr int words = 2; };
 template <> struct EntryOf<2> { using type = uint4;    static constexpr int words = 4; };
+constexpr uint32_t kNullCell = 0xffffffffu;                 // padding entry: skipped by the fold
+template <int NCH>
+__device__ __forceinline__ typename EntryOf<NCH>::type make_null_entry()
+{
+    if constexpr (NCH == 0) return kNullCell;
+    else if constexpr (NCH == 1) return make_uint2(kNullCell, 0u);
+    else return make_uint4(kNullCell, 0u, 0u, 0u);
+}
+// shared memory -> global memory through the bulk-copy engine (TMA; SASS UBLKCP.G.S); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_store(void* dst_global, const void* src_shared, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst_global), "r"(static_cast<uint32_t>(__cvta_generic_to_shared(src_shared))), "r"(bytes) : "memory");
+}
 template <int NCH>
 __device__ __forceinline__ typename EntryOf<NCH>::type make_entry(uint32_t cell, const float* v)
 {
@@ -50,16 +64,17 @@ __device__ __forceinline__ typename EntryOf<NCH>::type make_entry(uint32_t cell,
     else return make_uint4(cell, __float_as_uint(v[0]), __float_as_uint(v[1]), 0u);
 }
 
-// Exclusive scan of s_hist[0..nbins) into s_prefix, nbins <= kMaxBins = 4 * kBinThreads.
+// Exclusive scan of the counts s_hist[0..nbins), each rounded up to a multiple of `align` entries (so that
+// every bin's run starts 16-byte aligned in the staging buffer), into s_prefix; nbins <= 4 * kBinThreads.
 __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t* s_hist, uint32_t* s_prefix, int nbins,
-                                                    uint32_t* s_warp)
+                                                    uint32_t* s_warp, uint32_t align)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t v[4], sum = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int b = tid * 4 + k;
-        v[k] = b < nbins ? s_hist[b] : 0u;
+        v[k] = b < nbins ? ((s_hist[b] + align - 1) & ~(align - 1)) : 0u;
         sum += v[k];
     }
     uint32_t inc = sum;
@@ -111,20 +126,21 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
     uint32_t* s_open_fill = s_open_page + nbins;                          // [nbins]  memory for the life of the launch
     uint32_t* s_warp   = s_open_fill + nbins;                             // [32]
     using Entry = typename EntryOf<NCH>::type;
-    uint32_t* st_pos   = s_hist + ((nb4 + 7 * nbins + 32 + 3) & ~3);      // [chunk]  destination entry index (16-byte aligned)
-    Entry*    st_ent   = reinterpret_cast<Entry*>(st_pos + kBinChunk);    // [chunk]  {cell, values} in bin order
-    uint8_t*  st_pool  = reinterpret_cast<uint8_t*>(st_ent + kBinChunk);  // [chunk]
+    constexpr uint32_t kAlign = 16 / sizeof(Entry);                       // entries per 16 bytes: runs start and end on it
+    const uint32_t stride = (kBinChunk + static_cast<uint32_t>(nbins) * (kAlign - 1) + 3u) & ~3u;   // one staging buffer, 16-byte multiple
+    Entry* st_base = reinterpret_cast<Entry*>(s_hist + ((nb4 + 7 * nbins + 32 + 3) & ~3));   // [2][stride], 16-byte aligned
 
     const int tid = threadIdx.x;
     uint32_t* my_open_page = bt.open_page + static_cast<size_t>(blockIdx.x) * nbins;
     uint32_t* my_open_fill = bt.open_fill + static_cast<size_t>(blockIdx.x) * nbins;
     const size_t nchunks = (n + kBinChunk - 1) / kBinChunk;
     const bool multi_tile = g.tiles_x * g.tiles_y > 1;
-    const bool multi_pool = bt.bin_owner_shift >= 0;
     bool any_valid = false;
     for (int b = tid; b < nbins; b += kBinThreads) { s_open_page[b] = my_open_page[b]; s_open_fill[b] = my_open_fill[b]; }
 
-    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    int buf = 0;
+    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, buf ^= 1) {
+        Entry* st_ent = st_base + static_cast<size_t>(buf) * stride;      // {cell, values} of this chunk in bin order
         for (int b = tid; b < nbins; b += kBinThreads) s_hist[b] = 0;
         __syncthreads();
 
@@ -166,11 +182,14 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
         __syncthreads();
 
         // ---- where does each bin's run go?  (page chain of this CTA; at most two pages per run) ----
-        const uint32_t total = block_scan_bins(s_hist, s_prefix, nbins, s_warp);
-        __syncthreads();                                   // s_prefix[b] is read by another thread than its writer
+        block_scan_bins(s_hist, s_prefix, nbins, s_warp, kAlign);
+        // this staging buffer was the source of the bulk stores issued two chunks ago: they must have read it
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();                                   // (also: s_prefix[b] is read by another thread than its writer)
         for (int b = tid; b < nbins; b += kBinThreads) {
             const uint32_t cnt = s_hist[b];
             if (cnt == 0) continue;
+            const uint32_t cnt2 = (cnt + kAlign - 1) & ~(kAlign - 1);      // with the null entries that pad the run
             const int owner = bt.bin_owner_shift >= 0 ? static_cast<int>(static_cast<uint32_t>(b) / bt.bins_per_owner) : 0;
             const BinPool& pool = bt.pool[owner];
             uint32_t page = s_open_page[b], fill = s_open_fill[b];
@@ -181,44 +200,51 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
                 return pg;
             };
             if (page == kNoPage || fill == kBinPageEntries) { page = alloc(); fill = 0; }
-            const uint32_t len_a = min(cnt, kBinPageEntries - fill);
+            const uint32_t len_a = min(cnt2, kBinPageEntries - fill);      // fill, cnt2 and the page size are multiples of kAlign
             const uint32_t seg_a = page * kBinPageEntries + fill;
             uint32_t seg_b = 0;
-            s_pool[b] = static_cast<uint32_t>(owner);
             pool.page_fill[page] = fill + len_a;
             fill += len_a;
-            if (cnt > len_a) {
+            if (cnt2 > len_a) {
                 page = alloc();
-                fill = cnt - len_a;
+                fill = cnt2 - len_a;
                 seg_b = page * kBinPageEntries;
                 pool.page_fill[page] = fill;
             }
-            s_tab[b] = make_uint4(s_prefix[b], len_a, seg_a, seg_b - len_a);
+            const uint32_t off = s_prefix[b];
+            s_tab[b] = make_uint4(off, len_a, seg_a, seg_b);
+            s_pool[b] = static_cast<uint32_t>(owner) | (cnt2 << 8);
+            for (uint32_t k = cnt; k < cnt2; ++k) st_ent[off + k] = make_null_entry<NCH>();
             s_open_page[b] = page;
             s_open_fill[b] = fill;
         }
         __syncthreads();
 
-        // ---- counting sort into the staging arrays ----
+        // ---- counting sort into the staging buffer ----
 #pragma unroll
         for (int k = 0; k < kBinPts; ++k) {
             if (key[k] == 0xffffffffu) continue;
             const uint32_t bin = key[k] >> 13, rank = key[k] & 8191u;
-            const uint4 tb = s_tab[bin];
-            const uint32_t at = tb.x + rank;
-            st_pos[at] = (rank < tb.y ? tb.z : tb.w) + rank;
-            st_ent[at] = make_entry<NCH>(cell[k], val[k]);
-            if (multi_pool) st_pool[at] = static_cast<uint8_t>(s_pool[bin]);
+            st_ent[s_tab[bin].x + rank] = make_entry<NCH>(cell[k], val[k]);
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the bulk-copy engine
         __syncthreads();
 
-        // ---- copy out: consecutive threads = consecutive entries of one run = consecutive addresses ----
-        for (uint32_t t = tid; t < total; t += kBinThreads) {
-            const BinPool& pool = bt.pool[multi_pool ? st_pool[t] : 0];
-            reinterpret_cast<Entry*>(pool.ent)[st_pos[t]] = st_ent[t];
+        // ---- copy out: every run leaves as one or two bulk stores (TMA, UBLKCP): shared memory -> the owner's page,
+        //      local HBM or NVLink peer memory, in large packets and without occupying any thread ----
+        for (int b = tid; b < nbins; b += kBinThreads) {
+            if (s_hist[b] == 0) continue;
+            const uint4 tb = s_tab[b];
+            const uint32_t pw = s_pool[b];
+            const BinPool& pool = bt.pool[pw & 0xffu];
+            const uint32_t cnt2 = pw >> 8;
+            Entry* dst = reinterpret_cast<Entry*>(pool.ent);
+            bulk_store(dst + tb.z, st_ent + tb.x, tb.y * static_cast<uint32_t>(sizeof(Entry)));
+            if (cnt2 > tb.y) bulk_store(dst + tb.w, st_ent + tb.x + tb.y, (cnt2 - tb.y) * static_cast<uint32_t>(sizeof(Entry)));
         }
-        __syncthreads();
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");              // every store has landed before the kernel ends
     for (int b = tid; b < nbins; b += kBinThreads) { my_open_page[b] = s_open_page[b]; my_open_fill[b] = s_open_fill[b]; }
     if (!multi_tile) {
         if (__any_sync(0xffffffffu, any_valid) && (tid & 31) == 0 && touched[0] == 0) touched[0] = 1;
@@ -288,6 +314,7 @@ k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restric
             if constexpr (NCH == 0) cell = ent;
             else if constexpr (NCH == 1) { cell = ent.x; v[0] = __uint_as_float(ent.y); }
             else { cell = ent.x; v[0] = __uint_as_float(ent.y); v[1] = __uint_as_float(ent.z); }
+            if (cell == kNullCell) continue;                   // alignment padding of a run
             float add[kMaxAdd], mx[kMaxExt], mn[kMaxExt];
 #pragma unroll
             for (int j = 0; j < kMaxAdd; ++j) add[j] = (j < NADD) ? (L.add_src[j] < 0 ? 1.0f : pick(v, L.add_src[j])) : 0.0f;
@@ -353,8 +380,9 @@ bool bin_supported(const PassLayout& L) { return L.n_chan <= kBinMaxChan; }
 size_t bin_scatter_smem(int nbins, int n_chan)
 {
     const size_t nb4 = (2 * static_cast<size_t>(nbins) + 3) & ~size_t(3);
-    return ((nb4 + 7 * static_cast<size_t>(nbins) + 32 + 3) & ~size_t(3)) * 4 +
-           static_cast<size_t>(kBinChunk) * (4 + 4 * bin_entry_words(n_chan) + 1);
+    const size_t ew = bin_entry_words(n_chan), align = 4 / ew;              // entries per 16 bytes
+    const size_t stride = (kBinChunk + static_cast<size_t>(nbins) * (align - 1) + 3) & ~size_t(3);
+    return ((nb4 + 7 * static_cast<size_t>(nbins) + 32 + 3) & ~size_t(3)) * 4 + 2 * stride * ew * 4;
 }
 
 unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan)

@@ -36,6 +36,7 @@ struct BinTargets {
 };
 
 bool bin_supported(const PassLayout& L);
+uint64_t bin_capacity(uint64_t pages, int nbins, int n_chan);   // points that fit `pages` pages whatever their distribution
 size_t bin_scatter_smem(int nbins, int n_chan);
 unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan);
 // route n points once and append {cell, values} to the page chain of each point's bin

@@ -56,11 +56,17 @@ Status Engine::bin_setup(Pass& p)
         want = std::min<size_t>(size_t(1) << 31, free_b / 4 / entry_bytes);
     }
     want = std::max<size_t>(want, kBinPageEntries);
-    const size_t pages = want / kBinPageEntries + chains + 1;
+    // a run is padded to 16 bytes with null entries (at most align - 1 per bin and 4096-point chunk): size the
+    // pool so that `want` POINTS fit whatever their distribution
+    const size_t pad_align = 4 / static_cast<size_t>(bin_entry_words(p.layout.n_chan));
+    const size_t slots = (want + kBinPageEntries - 1) / kBinPageEntries * (kBinPageEntries + static_cast<size_t>(b.nbins) * (pad_align - 1));
+    const size_t pages = (slots + kBinPageEntries - 1) / kBinPageEntries + chains + 1;
     if (pages >= (size_t(1) << 20) * 1024 / kBinPageEntries * 4)     // entry indices are 32-bit
         return Status::error(PCR_INVALID_ARGUMENT, "pipeline: bin_pool_points too large");
     b.pool.pool_pages = static_cast<uint32_t>(pages);
-    b.capacity = (pages - chains - 1) * kBinPageEntries;
+    b.capacity = bin_capacity(pages - chains - 1, b.nbins, p.layout.n_chan);
+    if (b.capacity < kBinPageEntries)
+        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: bin_pool_points too small");
     const size_t entries = pages * kBinPageEntries;
     CU_TRY(cudaMalloc(&b.pool.ent, entries * entry_bytes));
     CU_TRY(cudaMalloc(&b.pool.page_bin, pages * 4));
@@ -82,6 +88,13 @@ Status Engine::bin_setup(Pass& p)
     return Status::success();
 }
 
+uint64_t bin_capacity(uint64_t pages, int nbins, int n_chan)
+{
+    const uint64_t align = 4 / static_cast<uint64_t>(bin_entry_words(n_chan));
+    const uint64_t slots = pages * kBinPageEntries;
+    return slots / (kBinPageEntries + static_cast<uint64_t>(nbins) * (align - 1)) * kBinPageEntries;
+}
+
 void Engine::bin_free(Pass& p)
 {
     BinState& b = p.bin;
@@ -100,6 +113,7 @@ Status Engine::bin_append(Pass& p, const uint8_t* mask, const double* dx, const 
     while (done < n) {
         if (b.pending >= b.capacity) ST_TRY(bin_flush(p));
         const size_t cnt = std::min<size_t>(n - done, b.capacity - b.pending);
+        if (cnt == 0) return Status::error(PCR_OUT_OF_MEMORY, "pipeline: the tile-binning entry pool cannot take any point");
         ChannelPtrs c2 = ch;
         for (int c = 0; c < p.layout.n_chan; ++c) c2.p[c] = ch.p[c] + done;
         BinTargets bt{};

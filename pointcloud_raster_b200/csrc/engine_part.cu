@@ -106,7 +106,8 @@ Status Engine::partition_setup()
             const uint64_t chains = static_cast<uint64_t>(b.grid) * b.nbins;
             for (int k = 0; k < world_; ++k) b.peer_pool[k].pool_pages = pages[i];
             b.pool.pool_pages = pages[i];
-            b.capacity = (static_cast<uint64_t>(pages[i]) - chains - 1) * kBinPageEntries / static_cast<uint64_t>(world_);
+            b.capacity = bin_capacity(static_cast<uint64_t>(pages[i]) - chains - 1, b.nbins, passes_[i].layout.n_chan) /
+                         static_cast<uint64_t>(world_);
         }
     }
     if (!e_delta_) CU_TRY(cudaEventCreateWithFlags(&e_delta_, cudaEventDisableTiming));
