@@ -427,6 +427,9 @@ Status Engine::init(const pcr_pipeline_desc& d)
     gp_.tile_w = grid_.tile_width; gp_.tile_h = grid_.tile_height;
     gp_.tiles_x = (grid_.width + grid_.tile_width - 1) / grid_.tile_width;
     gp_.tiles_y = (grid_.height + grid_.tile_height - 1) / grid_.tile_height;
+    auto log2_exact = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+    gp_.tile_w_shift = log2_exact(grid_.tile_width);
+    gp_.tile_h_shift = log2_exact(grid_.tile_height);
     gp_.exact_x = power_of_two(grid_.cell_size_x);
     gp_.exact_y = power_of_two(grid_.cell_size_y);
     n_tiles_ = gp_.tiles_x * gp_.tiles_y;
