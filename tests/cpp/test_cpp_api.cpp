@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <filesystem>
+#include <unistd.h>
 #include <iostream>
 #include <sstream>
 
@@ -402,6 +403,50 @@ TEST(grid_config_contract)
     EXPECT(!g.validate().ok());                 // no CRS
     g.crs = CRS::from_epsg(4326);
     EXPECT(g.validate().ok());
+}
+
+TEST(geotiff_lzw_overviews_and_tiled_writer)
+{
+    // include/pcr/io/grid_io.h:16-70: write_geotiff with the reference's default options (LZW), the tiled writer,
+    // read_geotiff_info / read_geotiff_band round trip
+    GridConfig g;
+    g.bounds = BBox{ 0.0, 0.0, 70.0, 45.0 };
+    g.tile_width = 32; g.tile_height = 16;
+    g.crs = CRS::from_epsg(32610);
+    g.compute_dimensions();
+    const fs::path dir = fs::temp_directory_path() / ("pcr_tif_" + std::to_string(::getpid()));
+    fs::create_directories(dir);
+    const std::string path = (dir / "tiled.tif").string();
+    GeoTiffOptions o;                                   // compress = "LZW"
+    auto w = TiledGeoTiffWriter::open(path, g, { "a", "b" }, o);
+    REQUIRE(w != nullptr);
+    std::vector<float> a(static_cast<size_t>(g.width) * g.height), b(a.size());
+    for (size_t i = 0; i < a.size(); ++i) { a[i] = static_cast<float>(i % 97) * 0.25f; b[i] = -static_cast<float>(i); }
+    for (int tr = 0; tr < g.tiles_y; ++tr)
+        for (int tc = 0; tc < g.tiles_x; ++tc) {
+            int c0, r0, cols, rows;
+            g.tile_cell_range(TileIndex{ tr, tc }, c0, r0, cols, rows);
+            std::vector<float> data(static_cast<size_t>(2) * cols * rows);
+            for (int r = 0; r < rows; ++r)
+                for (int c = 0; c < cols; ++c) {
+                    data[static_cast<size_t>(r) * cols + c] = a[static_cast<size_t>(r0 + r) * g.width + c0 + c];
+                    data[static_cast<size_t>(cols) * rows + static_cast<size_t>(r) * cols + c] = b[static_cast<size_t>(r0 + r) * g.width + c0 + c];
+                }
+            REQUIRE_OK(w->write_tile(TileIndex{ tr, tc }, data.data(), 2));
+        }
+    EXPECT(!w->write_tile(TileIndex{ 0, 0 }, a.data(), 3).ok());          // band count mismatch
+    REQUIRE_OK(w->close());
+    int width = 0, height = 0, nb = 0;
+    CRS crs; BBox bb;
+    REQUIRE_OK(read_geotiff_info(path, width, height, nb, crs, bb));
+    EXPECT(width == g.width && height == g.height && nb == 2 && crs.epsg == 32610);
+    std::vector<float> back(a.size());
+    REQUIRE_OK(read_geotiff_band(path, 0, back.data(), width, height));
+    EXPECT(back == a);
+    REQUIRE_OK(read_geotiff_band(path, 1, back.data(), width, height));
+    EXPECT(back == b);
+    EXPECT(!read_geotiff_band(path, 2, back.data(), width, height).ok());
+    fs::remove_all(dir);
 }
 
 }  // namespace
