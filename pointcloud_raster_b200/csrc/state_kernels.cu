@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace pcrb {
 
@@ -467,6 +468,14 @@ cudaError_t launch_filter_mask(cudaStream_t s, const FilterProgram& fp, size_t n
     return cudaGetLastError();
 }
 
+// CTAs per SM of the push and merge kernels.  They run beside the ingest kernel of the next step: a grid
+// that fills every SM slot (8 per SM) makes the three kernels take turns instead of overlapping.
+static int comm_ctas_per_sm()
+{
+    static const int v = [] { const char* e = std::getenv("PCR_COMM_CTAS_PER_SM"); const int k = e ? std::atoi(e) : 0; return k > 0 ? k : 8; }();
+    return v;
+}
+
 cudaError_t launch_push_slices(cudaStream_t s, uint32_t* state, uint32_t* touched, int n_tiles,
                                const GridParams& g, const PassLayout& L, const PushTargets& pt, const PeerSync& ps,
                                bool push_touched, bool signal, bool reset, int sm_count)
@@ -474,7 +483,7 @@ cudaError_t launch_push_slices(cudaStream_t s, uint32_t* state, uint32_t* touche
     const RecordIdentity id = identity_of(L);
     const size_t cells = static_cast<size_t>(g.width) * g.height;
     const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((cells + kThreads - 1) / kThreads,
-                                                                                     static_cast<size_t>(sm_count) * 8)));
+                                                                                     static_cast<size_t>(sm_count) * comm_ctas_per_sm())));
     switch (L.width) {
     case 1: k_push_slices<1><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal, reset, id); break;
     case 2: k_push_slices<2><<<grid, kThreads, 0, s>>>(state, touched, n_tiles, g, pt, ps, push_touched, signal, reset, id); break;
@@ -492,7 +501,7 @@ cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t
 {
     // count may be 0 (a rank that owns no rows): the handshake still has to happen
     const unsigned grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((count + kThreads - 1) / kThreads,
-                                                                                     static_cast<size_t>(sm_count) * 8)));
+                                                                                     static_cast<size_t>(sm_count) * comm_ctas_per_sm())));
     switch (L.width) {
     case 1: k_finalize_peer<1><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps, accum); break;
     case 2: k_finalize_peer<2><<<grid, kThreads, 0, s>>>(parts, part_cell0, cell0, count, out, band_stride, g, L, fp, ps, accum); break;
