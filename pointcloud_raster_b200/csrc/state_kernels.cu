@@ -469,10 +469,11 @@ cudaError_t launch_filter_mask(cudaStream_t s, const FilterProgram& fp, size_t n
 }
 
 // CTAs per SM of the push and merge kernels.  They run beside the ingest kernel of the next step: a grid
-// that fills every SM slot (8 per SM) makes the three kernels take turns instead of overlapping.
+// that fills every SM slot (8 per SM) makes the three kernels take turns instead of overlapping (N=2, config 2:
+// 88.8 us per step with 8, 85-86 us with 2-4, 116 us with 1 where the push itself becomes the bottleneck).
 static int comm_ctas_per_sm()
 {
-    static const int v = [] { const char* e = std::getenv("PCR_COMM_CTAS_PER_SM"); const int k = e ? std::atoi(e) : 0; return k > 0 ? k : 8; }();
+    static const int v = [] { const char* e = std::getenv("PCR_COMM_CTAS_PER_SM"); const int k = e ? std::atoi(e) : 0; return k > 0 ? k : 3; }();
     return v;
 }
 
