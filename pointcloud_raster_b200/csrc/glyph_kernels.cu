@@ -118,14 +118,49 @@ k_line(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const do
     const int stepx = ix0 < ix1 ? 1 : -1, stepy = iy0 < iy1 ? 1 : -1;
     int err = adx - ady, cx = ix0, cy = iy0;
     const int max_steps = 2 * (adx + ady) + 2;
+    // Two-word records (sum, weight): two horizontally adjacent cells whose first record is 16-byte aligned
+    // leave as ONE red.global.add.v4.f32 instead of two v2 — every cell of a line receives the same pair
+    // {v * 1, 1}.  The kernel sits on the per-SM reduction issue rate (225 G REDs/s), so fewer REDs is the lever;
+    // x-major lines pair up about 40 % of their cells.  Same adds per cell, hence identical results.
+    constexpr bool kPair = (NADD == 2) && !XACC;
+    bool pending = false;
+    int pcx = 0, pcy = 0;
+    float pa[kMaxAdd] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (kPair) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int src = L.add_src[j];
+            pa[j] = src < 0 ? 1.0f : __fmul_rn(src == 0 ? v[0] : src == 1 ? v[1] : src == 2 ? v[2] : v[3], 1.0f);
+        }
+    }
+    auto flush = [&]() {
+        if (pending) red_add2(reinterpret_cast<float*>(state) + (static_cast<size_t>(pcy) * g.width + pcx) * 2, pa[0], pa[1]);
+        pending = false;
+    };
     for (int s = 0; s <= max_steps; ++s) {
-        if (cx >= clip.c0 && cx < clip.c1 && cy >= clip.r0 && cy < clip.r1)
-            paint<NADD, XACC>(state, g, cx, cy, L, v, 1.0f, &xa);
+        if (cx >= clip.c0 && cx < clip.c1 && cy >= clip.r0 && cy < clip.r1) {
+            if constexpr (kPair) {
+                bool merged = false;
+                if (pending && cy == pcy && (cx == pcx + 1 || cx == pcx - 1)) {
+                    const int lo = min(cx, pcx);
+                    const size_t cell = static_cast<size_t>(cy) * g.width + lo;
+                    if ((cell & 1) == 0) {
+                        red_add4(reinterpret_cast<float*>(state) + cell * 2, pa[0], pa[1], pa[0], pa[1]);
+                        pending = false;
+                        merged = true;
+                    }
+                }
+                if (!merged) { flush(); pending = true; pcx = cx; pcy = cy; }
+            } else {
+                paint<NADD, XACC>(state, g, cx, cy, L, v, 1.0f, &xa);
+            }
+        }
         if (cx == ix1 && cy == iy1) break;
         const int e2 = 2 * err;
         if (e2 > -ady) { err -= ady; cx += stepx; }
         if (e2 <  adx) { err += adx; cy += stepy; }
     }
+    if constexpr (kPair) flush();
 }
 
 // ---------------------------------------------------------------------------
