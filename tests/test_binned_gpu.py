@@ -66,6 +66,26 @@ def test_binned_boundary_probes_and_two_channels(gpu_pcr, oracle):
     compare_bands(oracle, gd, [(x, y, ch)], specs, ref, got, "binned boundary + 2 channels")
 
 
+def test_binned_count_only_and_too_many_channels(gpu_pcr, oracle):
+    """Entries without a value (4-byte entries, runs padded to 4) and a pass with more channels than an entry
+    carries (falls back to the direct kernel even when the binned path is requested)."""
+    pcr = gpu_pcr
+    w, h = 190, 133
+    gc = make_grid(pcr, w, h, tile=64)
+    x, y, ch = uniform_cloud(120_000, w, h, seed=8, margin=-2.0)
+    rng = np.random.default_rng(4)
+    chans = {"value": ch["value"], "b": rng.normal(0, 2, len(x)).astype(np.float32),
+             "c": rng.uniform(0, 9, len(x)).astype(np.float32)}
+    gd = grid_desc(gc)
+    specs = [spec(pcr, "value", pcr.ReductionType.Count)]
+    got, _ = run_product(pcr, gc, [(x, y, chans)], specs, point_kernel=3, bin_cells_log2=7)
+    compare_bands(oracle, gd, [(x, y, chans)], specs, oracle.run(gd, [(x, y, chans)], specs), got, "binned Count only")
+    R = pcr.ReductionType
+    specs = [spec(pcr, "value", R.Sum), spec(pcr, "b", R.Max), spec(pcr, "c", R.Average)]
+    got, _ = run_product(pcr, gc, [(x, y, chans)], specs, point_kernel=3, bin_cells_log2=7)
+    compare_bands(oracle, gd, [(x, y, chans)], specs, oracle.run(gd, [(x, y, chans)], specs), got, "3 channels")
+
+
 def test_binned_many_ingests_refinalize_and_reset(gpu_pcr, oracle):
     """Entries pile up over several ingests; finalize folds them; later ingests keep accumulating; the pool
     is small enough that some ingests fold early; reset drops pending entries."""
