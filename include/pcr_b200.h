@@ -319,6 +319,12 @@ int pcr_comm_unique_id(void *id128);
 int pcr_comm_slice_rows(int32_t height, int32_t world_size, int32_t rank, int32_t *row0, int32_t *row1);
 int pcr_pipeline_comm_init(pcr_pipeline *p, const void *id128, int32_t rank, int32_t world_size);
 int pcr_pipeline_comm_barrier(pcr_pipeline *p);
+/* Tile-partitioned layout (comm_layout = 2), host arithmetic only: the bin geometry the engine derives for a grid of
+ * `cells` cells with `record_words`-word records (bin = 2^bin_shift consecutive cells; bin_cells_log2 = 0: records of a
+ * bin <= 64 MB, at most 1024 bins) and the row-major cell range [cell0, cell1) of the bins `rank` owns
+ * (ceil(num_bins / world_size) consecutive bins per rank). */
+int pcr_comm_partition_cells(uint64_t cells, int32_t record_words, int32_t bin_cells_log2, int32_t world_size, int32_t rank,
+                             int32_t *bin_shift, int32_t *num_bins, uint64_t *cell0, uint64_t *cell1);
 /* Row-major cell range [cell0, cell1) whose finalized bands THIS rank produces: the whole grid on one GPU,
  * the rank's row slice with replicated partial grids, the cells of its bins with the tile-partitioned layout.
  * With comm_root_only = 2 a rank's band arrays are valid for exactly this range. */

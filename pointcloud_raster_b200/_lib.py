@@ -133,6 +133,8 @@ SYMBOLS = [
     ("pcr_comm_slice_rows", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("pcr_pipeline_comm_init", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     ("pcr_pipeline_comm_barrier", C.c_int, [C.c_void_p]),
+    ("pcr_comm_partition_cells", C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("pcr_pipeline_owned_cells", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 ]
 

@@ -290,6 +290,21 @@ int pcr_pipeline_comm_init(pcr_pipeline* p, const void* id128, int32_t rank, int
     return GUARD(finish(eng(p)->comm_init(id128, rank, world_size)));
 }
 
+int pcr_comm_partition_cells(uint64_t cells, int32_t record_words, int32_t bin_cells_log2, int32_t world_size, int32_t rank,
+                             int32_t* bin_shift, int32_t* num_bins, uint64_t* cell0, uint64_t* cell1)
+{
+    if (!bin_shift || !num_bins || !cell0 || !cell1 || world_size < 1 || rank < 0 || rank >= world_size || cells == 0 ||
+        cells >= (uint64_t(1) << 32) || record_words < 1 || record_words > 8)
+        return fail(PCR_INVALID_ARGUMENT, "pcr_comm_partition_cells: bad arguments");
+    int shift = 0, nbins = 0;
+    pcrb::bin_geometry(static_cast<size_t>(cells), record_words, bin_cells_log2, shift, nbins);
+    uint32_t per = 0;
+    size_t c0 = 0, c1 = 0;
+    pcrb::bin_owner_cells(static_cast<size_t>(cells), shift, nbins, world_size, rank, per, c0, c1);
+    *bin_shift = shift; *num_bins = nbins; *cell0 = c0; *cell1 = c1;
+    return PCR_OK;
+}
+
 int pcr_pipeline_owned_cells(const pcr_pipeline* p, uint64_t* cell0, uint64_t* cell1)
 {
     NEED(p);

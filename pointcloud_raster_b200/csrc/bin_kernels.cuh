@@ -36,6 +36,9 @@ struct BinTargets {
 };
 
 bool bin_supported(const PassLayout& L);
+void bin_geometry(size_t cells, int record_words, int log2_req, int& shift, int& nbins);
+void bin_owner_cells(size_t cells, int shift, int nbins, int world, int rank, uint32_t& bins_per_owner,
+                     size_t& cell0, size_t& cell1);
 uint64_t bin_capacity(uint64_t pages, int nbins, int n_chan);   // points that fit `pages` pages whatever their distribution
 size_t bin_scatter_smem(int nbins, int n_chan);
 unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan);

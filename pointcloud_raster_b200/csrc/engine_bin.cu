@@ -33,16 +33,7 @@ Status Engine::bin_setup(Pass& p)
     // auto: only where the records cannot live in L2 (126 MB) anyway
     if (!forced && !(point_kernel_knob_ == 0 && state_bytes >= (size_t(256) << 20))) return Status::success();
 
-    // bin = 2^shift consecutive cells; auto: the records of a bin fill at most 64 MB, at most kMaxBins bins
-    int shift = bin_cells_log2_;
-    if (shift <= 0) {
-        shift = 4;
-        while ((size_t(2) << shift) * W * 4 <= (size_t(64) << 20)) ++shift;
-    }
-    shift = std::max(4, std::min(shift, 31));
-    while (((cells_ + (size_t(1) << shift) - 1) >> shift) > static_cast<size_t>(kMaxBins)) ++shift;
-    b.shift = shift;
-    b.nbins = static_cast<int>((cells_ + (size_t(1) << shift) - 1) >> shift);
+    bin_geometry(cells_, static_cast<int>(W), bin_cells_log2_, b.shift, b.nbins);
     b.grid = bin_scatter_grid(sm_count_, b.nbins, p.layout.n_chan);
     const size_t chains = static_cast<size_t>(b.grid) * b.nbins;
 
@@ -86,6 +77,32 @@ Status Engine::bin_setup(Pass& p)
     b.pending = 0;
     b.on = true;
     return Status::success();
+}
+
+// bin = 2^shift consecutive cells; auto (log2_req <= 0): the records of a bin fill at most 64 MB; never more
+// than kMaxBins bins
+void bin_geometry(size_t cells, int record_words, int log2_req, int& shift, int& nbins)
+{
+    shift = log2_req;
+    if (shift <= 0) {
+        shift = 4;
+        while ((size_t(2) << shift) * static_cast<size_t>(record_words) * 4 <= (size_t(64) << 20)) ++shift;
+    }
+    shift = std::max(4, std::min(shift, 31));
+    while (((cells + (size_t(1) << shift) - 1) >> shift) > static_cast<size_t>(kMaxBins)) ++shift;
+    nbins = static_cast<int>((cells + (size_t(1) << shift) - 1) >> shift);
+}
+
+// tile-partitioned layout: rank k owns bins [k * per, (k + 1) * per), per = ceil(nbins / world), i.e. the
+// row-major cell range [cell0, cell1)
+void bin_owner_cells(size_t cells, int shift, int nbins, int world, int rank, uint32_t& bins_per_owner,
+                     size_t& cell0, size_t& cell1)
+{
+    bins_per_owner = static_cast<uint32_t>((nbins + world - 1) / world);
+    const size_t bin0 = std::min<size_t>(nbins, static_cast<size_t>(rank) * bins_per_owner);
+    const size_t bin1 = std::min<size_t>(nbins, static_cast<size_t>(rank + 1) * bins_per_owner);
+    cell0 = std::min(cells, bin0 << shift);
+    cell1 = std::min(cells, bin1 << shift);
 }
 
 uint64_t bin_capacity(uint64_t pages, int nbins, int n_chan)

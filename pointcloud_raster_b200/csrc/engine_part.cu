@@ -61,11 +61,7 @@ Status Engine::partition_setup()
     size_t at = 0;
     for (Pass& p : passes_) {
         BinState& b = p.bin;
-        b.bins_per_owner = static_cast<uint32_t>((b.nbins + world_ - 1) / world_);
-        const size_t bin0 = std::min<size_t>(b.nbins, static_cast<size_t>(rank_) * b.bins_per_owner);
-        const size_t bin1 = std::min<size_t>(b.nbins, static_cast<size_t>(rank_ + 1) * b.bins_per_owner);
-        b.cell0 = std::min(cells_, bin0 << b.shift);
-        b.cell1 = std::min(cells_, bin1 << b.shift);
+        bin_owner_cells(cells_, b.shift, b.nbins, world_, rank_, b.bins_per_owner, b.cell0, b.cell1);
         for (int k = 0; k < world_; ++k) {
             BinPool q = b.pool;                      // same geometry (pool_pages) on every rank: same free-memory rule
             const std::vector<void*>& h = all[k];

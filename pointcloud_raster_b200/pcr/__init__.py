@@ -1009,6 +1009,15 @@ def comm_slice_rows(height: int, world_size: int, rank: int):
     return a.value, b.value
 
 
+def comm_partition_cells(cells: int, record_words: int, world_size: int, rank: int, bin_cells_log2: int = 0):
+    """Tile-partitioned layout: (bin_shift, num_bins, cell0, cell1) — bin = 2^bin_shift consecutive cells, `rank` owns
+    the row-major cells [cell0, cell1)."""
+    sh, nb, a, b = C.c_int32(0), C.c_int32(0), C.c_uint64(0), C.c_uint64(0)
+    check(lib.pcr_comm_partition_cells(int(cells), int(record_words), int(bin_cells_log2), int(world_size), int(rank),
+                                       C.byref(sh), C.byref(nb), C.byref(a), C.byref(b)))
+    return sh.value, nb.value, a.value, b.value
+
+
 def device_count() -> int:
     return int(lib.pcr_device_count())
 
@@ -1134,5 +1143,5 @@ __all__ = [
     'gaussian_splat_spec', 'line_splat_spec', 'GeoTiffOptions', 'write_geotiff',
     'read_geotiff_info', 'read_geotiff_band', 'TiledGeoTiffWriter', 'PointCloudInfo', 'read_point_cloud', 'write_point_cloud',
     'read_point_cloud_info', 'PointCloudReader',
-    'comm_unique_id', 'comm_slice_rows', 'device_count', 'device_name',
+    'comm_unique_id', 'comm_slice_rows', 'comm_partition_cells', 'device_count', 'device_name',
 ]

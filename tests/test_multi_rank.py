@@ -110,6 +110,96 @@ def test_combine_algorithm_gloo_world2(oracle):
     assert np.isnan(got[0][:16]).all()               # untouched north tiles: NaN on every rank's slice
 
 
+def _gloo_exchange_worker(rank, world, port, out_dir):
+    """The tile-partitioned layout restated on CPU: every rank routes its own points (oracle), sends each entry
+    {cell, value} to the rank that owns the entry's bin (ownership = the product's pcr_comm_partition_cells), the
+    owners fold what they received; no reduce."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import torch
+    import torch.distributed as dist
+    import oracle as orc
+    from pointcloud_raster_b200 import pcr
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    o = orc.Oracle()
+    w, h = 61, 47
+    gd = orc.GridDesc(0, 0, w, h, tile_width=16, tile_height=16)
+    rng = np.random.default_rng(321)
+    n = 30000
+    x, y = rng.uniform(-1, w + 1, n), rng.uniform(-1, h + 1, n)
+    v = rng.normal(0, 5, n).astype(np.float32)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    cell, _tile, valid = o.assign(gd, x[lo:hi], y[lo:hi])
+    valid = valid.astype(bool)
+    cell, vals = cell[valid].astype(np.int64), v[lo:hi][valid]
+    shift, nbins, c0, c1 = pcr.comm_partition_cells(w * h, 4, world, rank, bin_cells_log2=6)
+    owners = [pcr.comm_partition_cells(w * h, 4, world, r, bin_cells_log2=6)[2:] for r in range(world)]
+    assert owners[0][0] == 0 and owners[-1][1] == w * h and all(a[1] == b[0] for a, b in zip(owners, owners[1:]))
+    dest = np.searchsorted([a for a, _ in owners], cell, side="right") - 1            # owner of each entry's bin
+    assert all(((cell[dest == r] >> shift) * (1 << shift) >= owners[r][0]).all() for r in range(world))
+    # all-to-all of the entries (counts first, then payloads)
+    send = [torch.from_numpy(np.stack([cell[dest == r].astype(np.float64), vals[dest == r].astype(np.float64)], 1).copy())
+            for r in range(world)]
+    counts = torch.tensor([len(t) for t in send])
+    got_counts = torch.zeros(world, dtype=torch.long)
+    dist.all_to_all_single(got_counts, counts)
+    recv = [torch.empty((int(k), 2), dtype=torch.float64) for k in got_counts]
+    recv[rank] = send[rank]
+    ops = []
+    for peer in range(world):                       # gloo has no list all_to_all: point-to-point pairs
+        if peer == rank:
+            continue
+        ops += [dist.P2POp(dist.isend, send[peer], peer), dist.P2POp(dist.irecv, recv[peer], peer)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    ent = torch.cat(recv).numpy()
+    ec, ev = ent[:, 0].astype(np.int64), ent[:, 1].astype(np.float32)
+    assert ((ec >= c0) & (ec < c1)).all()                                        # only cells I own arrive here
+    cnt = np.bincount(ec - c0, minlength=c1 - c0).astype(np.float32)
+    mx = np.full(c1 - c0, -np.inf, np.float32)
+    np.maximum.at(mx, ec - c0, ev)
+    sm = np.bincount(ec - c0, weights=ev.astype(np.float64), minlength=c1 - c0)
+    np.savez(os.path.join(out_dir, f"own{rank}.npz"), c0=c0, c1=c1, cnt=cnt, mx=mx, sm=sm)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partitioned_exchange_algorithm_gloo_world2(oracle):
+    import torch.multiprocessing as mp
+    import oracle as orc
+    import make_golden as mg
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_gloo_exchange_worker, args=(world, _free_port(), d), nprocs=world, join=True)
+        parts = [np.load(os.path.join(d, f"own{r}.npz")) for r in range(world)]
+        w, h = 61, 47
+        cnt = np.concatenate([p["cnt"] for p in parts]).reshape(h, w)
+        mx = np.concatenate([p["mx"] for p in parts]).reshape(h, w)
+        sm = np.concatenate([p["sm"] for p in parts]).reshape(h, w)
+    gd = orc.GridDesc(0, 0, w, h, tile_width=16, tile_height=16)
+    rng = np.random.default_rng(321)
+    n = 30000
+    x, y = rng.uniform(-1, w + 1, n), rng.uniform(-1, h + 1, n)
+    v = rng.normal(0, 5, n).astype(np.float32)
+    specs = [mg.Spec("v", t) for t in (orc.COUNT, orc.MAX, orc.SUM)]
+    ref = oracle.run(gd, [(x, y, {"v": v})], specs)
+    has = cnt > 0
+    assert np.array_equal(np.isnan(ref[0]), ~has) and np.array_equal(ref[0][has], cnt[has])    # Count: exact
+    assert np.array_equal(ref[1][has], mx[has])                                                 # Max: exact
+    np.testing.assert_allclose(ref[2][has], sm[has], rtol=1e-5, atol=1e-4)
+
+
+def test_partition_cells_tile_the_grid(pcr):
+    for cells in (1, 17, 85581, 1_000_000, 400_000_000):
+        for world in (1, 2, 3, 8):
+            for log2 in (0, 6, 12):
+                edges = [pcr.comm_partition_cells(cells, 4, world, r, log2) for r in range(world)]
+                assert edges[0][2] == 0 and edges[-1][3] == cells
+                assert all(a[3] == b[2] for a, b in zip(edges, edges[1:]))
+                shift, nbins = edges[0][0], edges[0][1]
+                assert nbins <= 1024 and (nbins - 1) << shift < cells <= nbins << shift
+                assert all(e[2] % (1 << shift) == 0 or e[2] == cells for e in edges)   # slices start on bin boundaries
+
+
 def test_slice_rows_cover_grid(pcr):
     for h in (1, 2, 7, 37, 1000, 20000):
         for world in (1, 2, 3, 4, 8):
