@@ -194,9 +194,10 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
             const BinPool& pool = bt.pool[owner];
             uint32_t page = s_open_page[b], fill = s_open_fill[b];
             auto alloc = [&]() -> uint32_t {
-                uint32_t pg = atomicAdd(pool.next_page, 1u);            // (a remote atomic when the pool is a peer's)
-                if (pg >= pool.pool_pages) { *pool.overflow = 1u; pg = pool.pool_pages - 1; }
-                pool.page_bin[pg] = static_cast<uint32_t>(b);
+                uint32_t idx = atomicAdd(pool.next_page, 1u);           // always local memory (see BinPool)
+                if (idx >= pool.sub_pages) { *pool.overflow = 1u; idx = pool.sub_pages - 1; }
+                const uint32_t pg = pool.page_base + idx;
+                pool.page_bin[pg] = static_cast<uint32_t>(b);           // (a posted NVLink store when the pool is a peer's)
                 return pg;
             };
             if (page == kNoPage || fill == kBinPageEntries) { page = alloc(); fill = 0; }
@@ -252,15 +253,23 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
 }
 
 // ---- flush: order the pages by bin, then fold them ----
-__global__ void k_bin_page_count(const __grid_constant__ BinPool pool, uint32_t* __restrict__ bin_pages)
+// page p of the pool is in use iff it lies in the used prefix of its source's slice
+__device__ __forceinline__ bool page_used(const BinPool& pool, uint32_t p)
 {
-    const uint32_t np = min(*pool.next_page, pool.pool_pages);
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
-        atomicAdd(&bin_pages[pool.page_bin[p]], 1u);
+    const uint32_t r = p / pool.sub_pages;
+    return r < static_cast<uint32_t>(pool.n_src) && p - r * pool.sub_pages < min(pool.src_count[r], pool.sub_pages);
 }
 
-// single CTA: exclusive scan of bin_pages[0..nbins) -> bin_first; bin_pages becomes the running cursor
-__global__ void k_bin_page_scan(uint32_t* __restrict__ bin_pages, uint32_t* __restrict__ bin_first, int nbins)
+__global__ void k_bin_page_count(const __grid_constant__ BinPool pool, uint32_t* __restrict__ bin_pages)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pool.pool_pages; p += gridDim.x * blockDim.x)
+        if (page_used(pool, p)) atomicAdd(&bin_pages[pool.page_bin[p]], 1u);
+}
+
+// single CTA: exclusive scan of bin_pages[0..nbins) -> bin_first; bin_pages becomes the running cursor;
+// ctrl[3] = pages to fold
+__global__ void k_bin_page_scan(const __grid_constant__ BinPool pool, uint32_t* __restrict__ bin_pages,
+                                uint32_t* __restrict__ bin_first, int nbins)
 {
     __shared__ uint32_t s[kMaxBins];
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) s[b] = bin_pages[b];
@@ -268,6 +277,7 @@ __global__ void k_bin_page_scan(uint32_t* __restrict__ bin_pages, uint32_t* __re
     if (threadIdx.x == 0) {
         uint32_t run = 0;
         for (int b = 0; b < nbins; ++b) { const uint32_t c = s[b]; s[b] = run; run += c; }
+        pool.ctrl[3] = run;
     }
     __syncthreads();
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) { bin_first[b] = s[b]; bin_pages[b] = 0; }
@@ -276,8 +286,8 @@ __global__ void k_bin_page_scan(uint32_t* __restrict__ bin_pages, uint32_t* __re
 __global__ void k_bin_page_order(const __grid_constant__ BinPool pool, const uint32_t* __restrict__ bin_first,
                                  uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ order)
 {
-    const uint32_t np = min(*pool.next_page, pool.pool_pages);
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pool.pool_pages; p += gridDim.x * blockDim.x) {
+        if (!page_used(pool, p)) continue;
         const uint32_t b = pool.page_bin[p];
         order[bin_first[b] + atomicAdd(&bin_cursor[b], 1u)] = p;
     }
@@ -295,10 +305,10 @@ k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restric
     // (tools/micro/bin_locality.cu: 25 Gpts/s with the static stride, 72 Gpts/s when the pages in flight are
     // always the contiguous frontier of the bin-ordered list), and only a compact frontier keeps the
     // records of the bins being folded resident in L2.
-    const uint32_t np = min(*pool.next_page, pool.pool_pages);
+    const uint32_t np = pool.ctrl[3];
     __shared__ uint32_t s_next;
     for (;;) {
-        if (threadIdx.x == 0) s_next = atomicAdd(pool.next_page + 2, 1u);
+        if (threadIdx.x == 0) s_next = atomicAdd(pool.ctrl + 2, 1u);
         __syncthreads();
         const uint32_t i = s_next;
         __syncthreads();
@@ -331,7 +341,8 @@ k_bin_accumulate(const __grid_constant__ BinPool pool, const uint32_t* __restric
 __global__ void k_bin_reset(const __grid_constant__ BinPool pool, uint32_t* __restrict__ open_page, size_t n_open)
 {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i == 0) { pool.next_page[0] = 0; pool.next_page[2] = 0; }      // pages handed out, accumulate cursor
+    if (i == 0) { pool.ctrl[0] = 0; pool.ctrl[2] = 0; pool.ctrl[3] = 0; }   // pages handed out (one GPU), fold cursor, fold total
+    if (i < static_cast<size_t>(pool.n_src)) pool.src_count[i] = 0;
     for (size_t k = i; k < n_open; k += static_cast<size_t>(gridDim.x) * blockDim.x) open_page[k] = kNoPage;
 }
 
@@ -427,7 +438,7 @@ cudaError_t launch_bin_flush(cudaStream_t s, const BinPool& pool, int nbins, uin
 {
     const unsigned g1 = static_cast<unsigned>(sm_count) * 4;
     k_bin_page_count<<<g1, 256, 0, s>>>(pool, bin_pages);
-    k_bin_page_scan<<<1, 256, 0, s>>>(bin_pages, bin_first, nbins);
+    k_bin_page_scan<<<1, 256, 0, s>>>(pool, bin_pages, bin_first, nbins);
     k_bin_page_order<<<g1, 256, 0, s>>>(pool, bin_first, bin_pages, order);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -19,10 +19,22 @@ struct BinPool {
     uint32_t* ent;
     uint32_t* page_bin;                      // [pool_pages] bin a page belongs to
     uint32_t* page_fill;                     // [pool_pages] entries written to a page so far
-    uint32_t* next_page;                     // [0] pages handed out so far, [1] overflow flag, [2] cursor of the fold
-    uint32_t* overflow;                      // set to 1 if the pool ran out (entries were dropped)
+    // Control words.  The SCATTER side allocates pages with atomicAdd(next_page): on one GPU next_page is word [0]
+    // of the pool's own control block; in the tile-partitioned layout every source rank owns a fixed slice of
+    // every owner's pool (pages [page_base, page_base + sub_pages)) and next_page is a counter in the SOURCE's
+    // local memory — no remote atomic, whose round trip queues behind the posted stores on NVLink (measured: it
+    // tripled the time of the exchange at 8 GPUs).  The FOLD side (the owner) reads how many pages each source
+    // used from src_count[0..n_src) and uses ctrl[2] as its page cursor, ctrl[3] as the number of pages to fold.
+    uint32_t* next_page;                     // scatter: allocation counter of this (source, owner) pair
+    uint32_t* overflow;                      // set to 1 if the slice ran out (entries were dropped)
+    uint32_t* ctrl;                          // owner's control block: [0] next (one GPU) [1] overflow [2] cursor [3] total
+    uint32_t* src_count;                     // owner: pages used by each source, [n_src]
+    uint32_t  page_base;                     // scatter: first page of my slice of this pool
+    uint32_t  sub_pages;                     // pages per source slice (= pool_pages on one GPU)
+    int       n_src;
     uint32_t  pool_pages;
 };
+constexpr int kBinCtrlWords = 4 + kMaxParts;  // ctrl[4 + r] = src_count[r] in the partitioned layout
 
 // Where the scatter kernel sends a bin's entries.
 struct BinTargets {

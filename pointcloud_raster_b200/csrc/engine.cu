@@ -529,6 +529,8 @@ Status Engine::reset()
     for (Pass& p : passes_)
         if (p.bin.on) {
             CU_TRY(launch_bin_reset(compute_, p.bin.pool, p.bin.open_page, static_cast<size_t>(p.bin.grid) * p.bin.nbins, sm_count_));
+            if (p.bin.part_counters)
+                CU_TRY(cudaMemsetAsync(p.bin.part_counters, 0, static_cast<size_t>(world_) * 4 * sizeof(uint32_t), compute_));
             p.bin.pending = 0;
         }
     if (d_survivors_) CU_TRY(cudaMemsetAsync(d_survivors_, 0, sizeof(unsigned long long), compute_));

@@ -77,6 +77,7 @@ struct BinState {
     uint32_t bins_per_owner = 0;
     size_t cell0 = 0, cell1 = 0;
     BinPool peer_pool[kMaxParts] = {};
+    uint32_t* part_counters = nullptr;   // [world][4] local: {pages I took from my slice of owner k's pool, overflow, -, -}
 };
 
 // One fused pass: every reduction in it shares the glyph footprint.

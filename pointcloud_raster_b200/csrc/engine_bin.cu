@@ -62,9 +62,14 @@ Status Engine::bin_setup(Pass& p)
     CU_TRY(cudaMalloc(&b.pool.ent, entries * entry_bytes));
     CU_TRY(cudaMalloc(&b.pool.page_bin, pages * 4));
     CU_TRY(cudaMalloc(&b.pool.page_fill, pages * 4));
-    CU_TRY(cudaMalloc(&b.pool.next_page, 4 * sizeof(uint32_t)));
-    b.pool.overflow = b.pool.next_page + 1;
-    CU_TRY(cudaMemsetAsync(b.pool.next_page, 0, 4 * sizeof(uint32_t), compute_));
+    CU_TRY(cudaMalloc(&b.pool.ctrl, kBinCtrlWords * sizeof(uint32_t)));
+    CU_TRY(cudaMemsetAsync(b.pool.ctrl, 0, kBinCtrlWords * sizeof(uint32_t), compute_));
+    b.pool.next_page = b.pool.ctrl;              // one GPU: the pool is one slice, its counter is ctrl[0]
+    b.pool.overflow = b.pool.ctrl + 1;
+    b.pool.src_count = b.pool.ctrl;
+    b.pool.n_src = 1;
+    b.pool.page_base = 0;
+    b.pool.sub_pages = static_cast<uint32_t>(pages);
     CU_TRY(cudaMalloc(&b.bin_pages, static_cast<size_t>(b.nbins) * 4));
     CU_TRY(cudaMalloc(&b.bin_first, static_cast<size_t>(b.nbins) * 4));
     CU_TRY(cudaMemsetAsync(b.bin_pages, 0, static_cast<size_t>(b.nbins) * 4, compute_));
@@ -116,7 +121,7 @@ void Engine::bin_free(Pass& p)
 {
     BinState& b = p.bin;
     cudaFree(b.pool.ent);
-    cudaFree(b.pool.page_bin); cudaFree(b.pool.page_fill); cudaFree(b.pool.next_page);
+    cudaFree(b.pool.page_bin); cudaFree(b.pool.page_fill); cudaFree(b.pool.ctrl); cudaFree(b.part_counters);
     cudaFree(b.bin_pages); cudaFree(b.bin_first); cudaFree(b.order); cudaFree(b.open_page); cudaFree(b.open_fill);
     b = BinState{};
 }

@@ -52,7 +52,7 @@ Status Engine::partition_setup()
         mine.push_back(q.ent);
         mine.push_back(q.page_bin);
         mine.push_back(q.page_fill);
-        mine.push_back(q.next_page);
+        mine.push_back(q.ctrl);
     }
     std::vector<std::vector<void*>> all;
     ST_TRY(ipc_exchange(mine, all));
@@ -69,8 +69,7 @@ Status Engine::partition_setup()
             q.ent = static_cast<uint32_t*>(h[j++]);
             q.page_bin = static_cast<uint32_t*>(h[j++]);
             q.page_fill = static_cast<uint32_t*>(h[j++]);
-            q.next_page = static_cast<uint32_t*>(h[j++]);
-            q.overflow = q.next_page + 1;
+            q.ctrl = static_cast<uint32_t*>(h[j++]);
             b.peer_pool[k] = q;
         }
         at += 4;
@@ -82,9 +81,6 @@ Status Engine::partition_setup()
         CU_TRY(cudaMalloc(&p.d_delta[0], std::max<size_t>(b.cell1 - b.cell0, 1) * W * 4));
         p.d_state = p.d_delta[0];
         CU_TRY(launch_init_state(compute_, p.d_state, b.cell1 - b.cell0, p.layout));
-        // a rank may send at most capacity / world points between two finalizes: then no owner's pool can
-        // overflow even if every point of every rank lands in its bins
-        b.capacity /= static_cast<uint64_t>(world_);
     }
     // the pools' geometry must agree (pool_pages is derived from each rank's free memory)
     {
@@ -100,11 +96,32 @@ Status Engine::partition_setup()
         for (size_t i = 0; i < passes_.size(); ++i) {
             BinState& b = passes_[i].bin;
             const uint64_t chains = static_cast<uint64_t>(b.grid) * b.nbins;
-            for (int k = 0; k < world_; ++k) b.peer_pool[k].pool_pages = pages[i];
-            b.pool.pool_pages = pages[i];
-            b.capacity = bin_capacity(static_cast<uint64_t>(pages[i]) - chains - 1, b.nbins, passes_[i].layout.n_chan) /
-                         static_cast<uint64_t>(world_);
+            // Every source rank owns a fixed slice of every owner's pool and allocates pages from it with a counter
+            // in its OWN memory: no remote atomic anywhere.  A slice must take all the points a rank may send
+            // between two finalizes even if every one of them lands on one owner: capacity = what one slice holds.
+            const uint32_t slice = pages[i] / static_cast<uint32_t>(world_);
+            if (slice <= chains + 1)
+                return Status::error(PCR_OUT_OF_MEMORY, "pipeline: tile-partitioned layout: the entry pool is too small to be "
+                                                        "sliced over the ranks; raise bin_pool_points");
+            if (!b.part_counters) CU_TRY(cudaMalloc(&b.part_counters, static_cast<size_t>(world_) * 4 * sizeof(uint32_t)));
+            CU_TRY(cudaMemsetAsync(b.part_counters, 0, static_cast<size_t>(world_) * 4 * sizeof(uint32_t), compute_));
+            for (int k = 0; k < world_; ++k) {
+                BinPool& q = b.peer_pool[k];
+                q.pool_pages = pages[i];
+                q.sub_pages = slice;
+                q.page_base = static_cast<uint32_t>(rank_) * slice;
+                q.next_page = b.part_counters + static_cast<size_t>(k) * 4;     // LOCAL counter for (me, owner k)
+                q.overflow = q.next_page + 1;
+                q.n_src = world_;
+                q.src_count = q.ctrl + 4;                                        // owner k's per-source page counts (peer memory)
+            }
+            b.pool.pool_pages = pages[i];                                        // my own pool, as the fold sees it
+            b.pool.sub_pages = slice;
+            b.pool.n_src = world_;
+            b.pool.src_count = b.pool.ctrl + 4;
+            b.capacity = bin_capacity(static_cast<uint64_t>(slice) - chains - 1, b.nbins, passes_[i].layout.n_chan);
         }
+        CU_TRY(cudaStreamSynchronize(compute_));
     }
     if (!e_delta_) CU_TRY(cudaEventCreateWithFlags(&e_delta_, cudaEventDisableTiming));
     partition_ = true;
@@ -163,7 +180,15 @@ Status Engine::finalize_multi_part()
     {
         PushTargets tg{};
         for (int k = 0; k < world_; ++k) tg.touched_stage[k] = peer_[k].touched_stage;
-        CU_TRY(launch_push_touched(compute_, d_touched_, n_tiles_, tg, pf, epoch_));
+        PartCounts pc{};
+        pc.n_pass = static_cast<int>(std::min<size_t>(passes_.size(), 4));
+        for (int i = 0; i < pc.n_pass; ++i) {
+            BinState& b = passes_[i].bin;
+            pc.local[i] = b.part_counters;
+            pc.my_overflow[i] = b.pool.ctrl + 1;
+            for (int k = 0; k < world_; ++k) pc.owner_count[i][k] = b.peer_pool[k].ctrl + 4 + rank_;
+        }
+        CU_TRY(launch_push_touched(compute_, d_touched_, n_tiles_, tg, pf, epoch_, pc));
         ++launches_;
     }
     prof_end(compute_);

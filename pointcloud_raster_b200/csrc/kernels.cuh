@@ -142,8 +142,16 @@ cudaError_t launch_push_slices(cudaStream_t s, uint32_t* state, uint32_t* touche
 
 // partition mode: my touched-tile flags into everyone's staging (slot = my rank), then phase 0 of `epoch`
 // on every rank ("everything this stream wrote into your memory so far has landed")
+// ... and, per binned pass, how many pages of my slice of every owner's pool I used (local counters -> the owners'
+// src_count words; the local counters go back to zero; my overflow flags are folded into my own pool's flag)
+struct PartCounts {
+    int n_pass;
+    uint32_t* local[4];                  // [world][4] local counters of pass i
+    uint32_t* my_overflow[4];            // my own pool's overflow word
+    uint32_t* owner_count[4][kMaxParts]; // where rank k keeps my page count
+};
 cudaError_t launch_push_touched(cudaStream_t s, const uint32_t* touched, int n_tiles, const PushTargets& pt,
-                                const PeerFlags& pf, uint32_t epoch);
+                                const PeerFlags& pf, uint32_t epoch, const PartCounts& pc);
 // store `epoch` into slot (phase, my rank) of every rank's flag array (system-scope release)
 cudaError_t launch_peer_signal(cudaStream_t s, const PeerFlags& pf, int phase, uint32_t epoch);
 // wait until every rank's slot of `phase` in MY flag array has reached `epoch`

@@ -363,11 +363,19 @@ __global__ void k_peer_signal(const __grid_constant__ PeerFlags pf, int phase, u
 }
 
 __global__ void k_push_touched(const uint32_t* __restrict__ touched, int n_tiles, const __grid_constant__ PushTargets pt,
-                               const __grid_constant__ PeerFlags pf, uint32_t epoch)
+                               const __grid_constant__ PeerFlags pf, uint32_t epoch, const __grid_constant__ PartCounts pc)
 {
     for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
         const uint32_t v = touched[t];
         for (int k = 0; k < pf.n; ++k) pt.touched_stage[k][static_cast<size_t>(pf.rank) * n_tiles + t] = v;
+    }
+    // pages I used in my slice of every owner's pool -> that owner; my counters start the next epoch from zero
+    for (int j = threadIdx.x; j < pc.n_pass * pf.n; j += blockDim.x) {
+        const int i = j / pf.n, k = j - i * pf.n;
+        uint32_t* c = pc.local[i] + k * 4;
+        *pc.owner_count[i][k] = c[0];
+        if (c[1]) *pc.my_overflow[i] = 1u;
+        c[0] = 0; c[1] = 0;
     }
     __syncthreads();
     if (threadIdx.x < pf.n) {
@@ -514,9 +522,9 @@ cudaError_t launch_finalize_peer(cudaStream_t s, const StateParts& parts, size_t
 }
 
 cudaError_t launch_push_touched(cudaStream_t s, const uint32_t* touched, int n_tiles, const PushTargets& pt,
-                                const PeerFlags& pf, uint32_t epoch)
+                                const PeerFlags& pf, uint32_t epoch, const PartCounts& pc)
 {
-    k_push_touched<<<1, 256, 0, s>>>(touched, n_tiles, pt, pf, epoch);
+    k_push_touched<<<1, 256, 0, s>>>(touched, n_tiles, pt, pf, epoch, pc);
     return cudaGetLastError();
 }
 
