@@ -31,10 +31,12 @@ using point_impl::RecordShape;
 using point_impl::pick;
 using point_impl::update_record;
 
-constexpr int kBinThreads = 512;                          // 2 CTAs per SM (<= 64 registers): 32 warps hide the
-constexpr int kBinPts = 8;                                // load -> sort -> store phases of each other
-constexpr int kBinChunk = kBinThreads * kBinPts;          // 4096 = kBinPageEntries
-static_assert(kBinChunk == static_cast<int>(kBinPageEntries), "a chunk's run must fit two pages");
+// A scatter CTA has THREADS threads and stages THREADS * kBinPts points per chunk; 32 warps per SM either way
+// (<= 64 registers): 2 CTAs of 512 threads or 4 CTAs of 256, whose load -> sort -> store phases hide each other.
+constexpr int kBinPts = 8;
+constexpr int kBinThreadsMax = 512;
+static_assert(kBinThreadsMax * kBinPts <= static_cast<int>(kBinPageEntries), "a chunk's run must fit two pages");
+static_assert(kBinPadChunk <= 256 * kBinPts, "capacity formulas assume the smallest chunk");
 constexpr uint32_t kNoPage = 0xffffffffu;
 
 // entry = {cell, values...} as one vector (see BinPool::ent)
@@ -66,6 +68,7 @@ __device__ __forceinline__ typename EntryOf<NCH>::type make_entry(uint32_t cell,
 
 // Exclusive scan of the counts s_hist[0..nbins), each rounded up to a multiple of `align` entries (so that
 // every bin's run starts 16-byte aligned in the staging buffer), into s_prefix; nbins <= 4 * kBinThreads.
+template <int kBinThreads>
 __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t* s_hist, uint32_t* s_prefix, int nbins,
                                                     uint32_t* s_warp, uint32_t align)
 {
@@ -107,12 +110,13 @@ __device__ __forceinline__ uint32_t block_scan_bins(const uint32_t* s_hist, uint
 
 // One CTA = a persistent worker with its own page chain per bin (open_page / open_fill rows in global
 // memory survive from launch to launch, so a chain's only partly filled page is its last one).
-template <int NCH, bool EXACT>
-__global__ void __launch_bounds__(kBinThreads, 2)
+template <int NCH, bool EXACT, int kBinThreads>
+__global__ void __launch_bounds__(kBinThreads, 1024 / kBinThreads)
 k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, const double* __restrict__ ys,
               const __grid_constant__ ChannelPtrs ch, size_t n, const __grid_constant__ GridParams g,
-              const __grid_constant__ BinTargets bt, uint32_t* __restrict__ touched)
+              const __grid_constant__ BinTargets bt, uint32_t* __restrict__ touched, int prefetch_next)
 {
+    constexpr int kBinChunk = kBinThreads * kBinPts;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbins = bt.nbins;
     uint32_t* s_hist   = reinterpret_cast<uint32_t*>(smem_raw);          // [nbins]  points of this chunk per bin
@@ -135,6 +139,8 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
     uint32_t* my_open_fill = bt.open_fill + static_cast<size_t>(blockIdx.x) * nbins;
     const size_t nchunks = (n + kBinChunk - 1) / kBinChunk;
     const bool multi_tile = g.tiles_x * g.tiles_y > 1;
+    const bool few_tiles = g.tiles_x * g.tiles_y <= 32;    // touched tiles collected in a register, flagged once at the end
+    uint32_t tile_bits = 0;
     bool any_valid = false;
     for (int b = tid; b < nbins; b += kBinThreads) { s_open_page[b] = my_open_page[b]; s_open_fill[b] = my_open_fill[b]; }
 
@@ -148,41 +154,64 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
         uint32_t cell[kBinPts], key[kBinPts];       // key = bin << 13 | rank  (rank < 4096), or ~0 = dropped
         float val[kBinPts][NCH > 0 ? NCH : 1];
         const size_t base = chunk * kBinChunk + tid;
+        // FULL: the whole chunk lies inside the cloud and no filter mask is set (every chunk but the last one of an
+        // unfiltered ingest) — no per-point bounds or mask tests
+        auto route_chunk = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-        for (int q = 0; q < kBinPts; q += 4) {
-            double x[4], y[4];
-            bool live[4];
+            for (int q = 0; q < kBinPts; q += 4) {
+                double x[4], y[4];
+                bool live[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const size_t i = base + static_cast<size_t>(q + u) * kBinThreads;
-                live[u] = i < n && (mask == nullptr || mask[i] != 0);
-                x[u] = live[u] ? ldg_stream_d(xs + i) : 0.0;
-                y[u] = live[u] ? ldg_stream_d(ys + i) : 0.0;
+                for (int u = 0; u < 4; ++u) {
+                    const size_t i = base + static_cast<size_t>(q + u) * kBinThreads;
+                    live[u] = FULL || (i < n && (mask == nullptr || mask[i] != 0));
+                    x[u] = live[u] ? ldg_stream_d(xs + i) : 0.0;
+                    y[u] = live[u] ? ldg_stream_d(ys + i) : 0.0;
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) val[q + u][c] = live[u] ? ldg_stream_f(ch.p[c] + i) : 0.0f;
-            }
+                    for (int c = 0; c < NCH; ++c) val[q + u][c] = live[u] ? ldg_stream_f(ch.p[c] + i) : 0.0f;
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int col = 0, row = 0;
-                const bool ok = live[u] && route_cell<EXACT>(g, x[u], y[u], col, row);
-                const uint32_t c = static_cast<uint32_t>(row) * static_cast<uint32_t>(g.width) + static_cast<uint32_t>(col);
-                cell[q + u] = c;
-                key[q + u] = 0xffffffffu;
-                if (ok) {
-                    const uint32_t bin = c >> bt.shift;
-                    key[q + u] = (bin << 13) | atomicAdd(&s_hist[bin], 1u);
-                    any_valid = true;
-                    if (multi_tile) {                    // touched-tile rule, tile_manager.cpp:437-444
-                        const int t = tile_of(g, col, row);
-                        if (touched[t] == 0) touched[t] = 1;
+                for (int u = 0; u < 4; ++u) {
+                    int col = 0, row = 0;
+                    const bool ok = route_cell<EXACT>(g, x[u], y[u], col, row) && live[u];
+                    const uint32_t c = static_cast<uint32_t>(row) * static_cast<uint32_t>(g.width) + static_cast<uint32_t>(col);
+                    cell[q + u] = c;
+                    key[q + u] = 0xffffffffu;
+                    if (ok) {
+                        const uint32_t bin = c >> bt.shift;
+                        key[q + u] = (bin << 13) | atomicAdd(&s_hist[bin], 1u);
+                        any_valid = true;
+                        if (multi_tile) {                    // touched-tile rule, tile_manager.cpp:437-444
+                            const int t = tile_of(g, col, row);
+                            if (few_tiles) tile_bits |= 1u << t;
+                            else if (touched[t] == 0) touched[t] = 1;
+                        }
                     }
+                }
+            }
+        };
+        if (mask == nullptr && (chunk + 1) * kBinChunk <= n) route_chunk(std::true_type{});
+        else route_chunk(std::false_type{});
+        if (prefetch_next) {
+            // pull the next chunk of this CTA into L2 while this one is sorted and stored (one 128-byte line per
+            // instruction: x and y are kBinChunk / 16 lines each, a value channel kBinChunk / 32)
+            const size_t nb = (chunk + gridDim.x) * kBinChunk;
+            constexpr int kLines = kBinChunk / 16;            // = kBinThreads / 2
+            const int l = tid < kLines ? tid : tid - kLines;
+            const size_t i = nb + static_cast<size_t>(l) * 16;
+            if (i < n) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"((tid < kLines ? xs : ys) + i));
+                if (NCH > 0 && (l & 1) == 0) {
+                    const int c = tid < kLines ? 0 : 1;
+                    if (c < NCH) asm volatile("prefetch.global.L2 [%0];" :: "l"(ch.p[c] + i));
                 }
             }
         }
         __syncthreads();
 
         // ---- where does each bin's run go?  (page chain of this CTA; at most two pages per run) ----
-        block_scan_bins(s_hist, s_prefix, nbins, s_warp, kAlign);
+        block_scan_bins<kBinThreads>(s_hist, s_prefix, nbins, s_warp, kAlign);
         // this staging buffer was the source of the bulk stores issued two chunks ago: they must have read it
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncthreads();                                   // (also: s_prefix[b] is read by another thread than its writer)
@@ -249,6 +278,10 @@ k_bin_scatter(const uint8_t* __restrict__ mask, const double* __restrict__ xs, c
     for (int b = tid; b < nbins; b += kBinThreads) { my_open_page[b] = s_open_page[b]; my_open_fill[b] = s_open_fill[b]; }
     if (!multi_tile) {
         if (__any_sync(0xffffffffu, any_valid) && (tid & 31) == 0 && touched[0] == 0) touched[0] = 1;
+    } else if (few_tiles) {
+        tile_bits = __reduce_or_sync(0xffffffffu, tile_bits);
+        if ((tid & 31) == 0)
+            for (uint32_t m = tile_bits; m; m &= m - 1) { const int t = __ffs(m) - 1; if (touched[t] == 0) touched[t] = 1; }
     }
 }
 
@@ -388,37 +421,43 @@ cudaError_t acc_max(cudaStream_t s, unsigned grid, const BinPool& pool, const ui
 
 bool bin_supported(const PassLayout& L) { return L.n_chan <= kBinMaxChan; }
 
-size_t bin_scatter_smem(int nbins, int n_chan)
+size_t bin_scatter_smem(int nbins, int n_chan, int threads)
 {
+    const size_t kBinChunk = static_cast<size_t>(threads) * kBinPts;
     const size_t nb4 = (2 * static_cast<size_t>(nbins) + 3) & ~size_t(3);
     const size_t ew = bin_entry_words(n_chan), align = 4 / ew;              // entries per 16 bytes
     const size_t stride = (kBinChunk + static_cast<size_t>(nbins) * (align - 1) + 3) & ~size_t(3);
     return ((nb4 + 7 * static_cast<size_t>(nbins) + 32 + 3) & ~size_t(3)) * 4 + 2 * stride * ew * 4;
 }
 
-unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan)
+unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan, int threads)
 {
-    // CTAs per SM by shared memory (227 KB usable), at most 2 (64 registers x 512 threads each)
-    const size_t per = bin_scatter_smem(nbins, n_chan);
-    const unsigned by_smem = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / per)));
+    // CTAs per SM by shared memory (227 KB usable), at most 1024 threads (64 registers each)
+    const size_t per = bin_scatter_smem(nbins, n_chan, threads);
+    const size_t by_threads = 1024 / static_cast<size_t>(threads);
+    const unsigned by_smem = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(by_threads, (220 * 1024) / per)));
     return static_cast<unsigned>(sm_count) * by_smem;
 }
 
 cudaError_t launch_bin_scatter(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                const ChannelPtrs& ch, size_t n, const GridParams& g, const PassLayout& L,
-                               const BinTargets& bt, uint32_t* touched, unsigned grid)
+                               const BinTargets& bt, uint32_t* touched, unsigned grid, int threads)
 {
     if (n == 0) return cudaSuccess;
-    const size_t smem = bin_scatter_smem(bt.nbins, L.n_chan);
+    if (threads != 256 && threads != 512) return cudaErrorInvalidValue;
+    const size_t smem = bin_scatter_smem(bt.nbins, L.n_chan, threads);
     const bool exact = g.exact_x && g.exact_y;
-#define PCR_BIN_LAUNCH(NCH, EX)                                                                             \
+    const int pf = 1;       // L2 prefetch of the CTA's next chunk: 8.3 -> 7.4 ms per 1B points (profiles/r02s3_bin_sweep.txt)
+#define PCR_BIN_LAUNCH_T(NCH, EX, T)                                                                        \
     do {                                                                                                    \
-        auto kern = k_bin_scatter<NCH, EX>;                                                                 \
+        auto kern = k_bin_scatter<NCH, EX, T>;                                                              \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                              static_cast<int>(smem));                                      \
         if (e != cudaSuccess) return e;                                                                     \
-        kern<<<grid, kBinThreads, smem, s>>>(mask, x, y, ch, n, g, bt, touched);                            \
+        kern<<<grid, T, smem, s>>>(mask, x, y, ch, n, g, bt, touched, pf);                                  \
     } while (0)
+#define PCR_BIN_LAUNCH(NCH, EX)                                                                             \
+    do { if (threads == 256) PCR_BIN_LAUNCH_T(NCH, EX, 256); else PCR_BIN_LAUNCH_T(NCH, EX, 512); } while (0)
     switch (L.n_chan * 2 + (exact ? 1 : 0)) {
     case 0: PCR_BIN_LAUNCH(0, false); break;
     case 1: PCR_BIN_LAUNCH(0, true); break;
@@ -429,6 +468,7 @@ cudaError_t launch_bin_scatter(cudaStream_t s, const uint8_t* mask, const double
     default: return cudaErrorInvalidValue;
     }
 #undef PCR_BIN_LAUNCH
+#undef PCR_BIN_LAUNCH_T
     return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 namespace pcrb {
 
 constexpr uint32_t kBinPageEntries = 4096;   // entries per page (= points per scatter chunk)
+constexpr uint32_t kBinPadChunk = 2048;      // smallest scatter chunk: every bin's run of a chunk is padded to 16 bytes
 constexpr int kMaxBins = 1024;
 constexpr int kBinMaxChan = 2;               // value channels an entry can carry
 inline int bin_entry_words(int n_chan) { return n_chan == 0 ? 1 : n_chan == 1 ? 2 : 4; }
@@ -52,12 +53,15 @@ void bin_geometry(size_t cells, int record_words, int log2_req, int& shift, int&
 void bin_owner_cells(size_t cells, int shift, int nbins, int world, int rank, uint32_t& bins_per_owner,
                      size_t& cell0, size_t& cell1);
 uint64_t bin_capacity(uint64_t pages, int nbins, int n_chan);   // points that fit `pages` pages whatever their distribution
-size_t bin_scatter_smem(int nbins, int n_chan);
-unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan);
+// scatter CTA = `threads` (256 or 512) threads staging 8 points each; 1024 threads per SM either way
+constexpr int kBinThreadsLocal = 256;        // one GPU: 4 CTAs per SM (8.3 -> 6.9 ms per 1B points with the L2 prefetch)
+constexpr int kBinThreadsPeer = 512;         // tile-partitioned layout: longer runs per bulk store over NVLink
+size_t bin_scatter_smem(int nbins, int n_chan, int threads);
+unsigned bin_scatter_grid(int sm_count, int nbins, int n_chan, int threads);
 // route n points once and append {cell, values} to the page chain of each point's bin
 cudaError_t launch_bin_scatter(cudaStream_t s, const uint8_t* mask, const double* x, const double* y,
                                const ChannelPtrs& ch, size_t n, const GridParams& g, const PassLayout& L,
-                               const BinTargets& bt, uint32_t* touched, unsigned grid);
+                               const BinTargets& bt, uint32_t* touched, unsigned grid, int threads);
 // fold every pending entry of `pool` into `state` (record of global cell c at state[(c - cell_base) * W]),
 // bin by bin, and empty the pool
 cudaError_t launch_bin_flush(cudaStream_t s, const BinPool& pool, int nbins, uint32_t* bin_pages, uint32_t* bin_first,

@@ -70,6 +70,7 @@ struct BinState {
     uint32_t *bin_pages = nullptr, *bin_first = nullptr, *order = nullptr;
     uint32_t *open_page = nullptr, *open_fill = nullptr;   // [grid][nbins] chains of this rank's scatter CTAs
     unsigned grid = 0;
+    int threads = 0;                // scatter CTA size (kBinThreadsLocal; kBinThreadsPeer in the tile-partitioned layout)
     uint64_t pending = 0;           // points appended since the last flush (upper bound of entries)
     uint64_t capacity = 0;          // points the pool takes whatever their distribution over the bins
     // N>1, tile-partitioned layout (engine_part.cu): owner of a bin = bin / bins_per_owner; this rank holds

@@ -34,7 +34,8 @@ Status Engine::bin_setup(Pass& p)
     if (!forced && !(point_kernel_knob_ == 0 && state_bytes >= (size_t(256) << 20))) return Status::success();
 
     bin_geometry(cells_, static_cast<int>(W), bin_cells_log2_, b.shift, b.nbins);
-    b.grid = bin_scatter_grid(sm_count_, b.nbins, p.layout.n_chan);
+    b.threads = kBinThreadsLocal;
+    b.grid = bin_scatter_grid(sm_count_, b.nbins, p.layout.n_chan, b.threads);
     const size_t chains = static_cast<size_t>(b.grid) * b.nbins;
 
     // pool size: every chain ends in one partly filled page, all other pages are full, so T points need at
@@ -47,13 +48,19 @@ Status Engine::bin_setup(Pass& p)
         want = std::min<size_t>(size_t(1) << 31, free_b / 4 / entry_bytes);
     }
     want = std::max<size_t>(want, kBinPageEntries);
-    // a run is padded to 16 bytes with null entries (at most align - 1 per bin and 4096-point chunk): size the
+    // a run is padded to 16 bytes with null entries (at most align - 1 per bin and scatter chunk): size the
     // pool so that `want` POINTS fit whatever their distribution
     const size_t pad_align = 4 / static_cast<size_t>(bin_entry_words(p.layout.n_chan));
-    const size_t slots = (want + kBinPageEntries - 1) / kBinPageEntries * (kBinPageEntries + static_cast<size_t>(b.nbins) * (pad_align - 1));
-    const size_t pages = (slots + kBinPageEntries - 1) / kBinPageEntries + chains + 1;
-    if (pages >= (size_t(1) << 20) * 1024 / kBinPageEntries * 4)     // entry indices are 32-bit
-        return Status::error(PCR_INVALID_ARGUMENT, "pipeline: bin_pool_points too large");
+    const size_t max_pages = (size_t(1) << 32) / kBinPageEntries;                // entry indices are 32-bit
+    size_t pages = 0;
+    for (;;) {
+        const size_t slots = (want + kBinPadChunk - 1) / kBinPadChunk * (kBinPadChunk + static_cast<size_t>(b.nbins) * (pad_align - 1));
+        pages = (slots + kBinPageEntries - 1) / kBinPageEntries + chains + 1;
+        if (pages < max_pages) break;
+        if (bin_pool_points_ != 0 || want <= kBinPageEntries)
+            return Status::error(PCR_INVALID_ARGUMENT, "pipeline: bin_pool_points too large");
+        want -= want / 8;                                                        // auto: the largest pool that can be indexed
+    }
     b.pool.pool_pages = static_cast<uint32_t>(pages);
     b.capacity = bin_capacity(pages - chains - 1, b.nbins, p.layout.n_chan);
     if (b.capacity < kBinPageEntries)
@@ -114,7 +121,7 @@ uint64_t bin_capacity(uint64_t pages, int nbins, int n_chan)
 {
     const uint64_t align = 4 / static_cast<uint64_t>(bin_entry_words(n_chan));
     const uint64_t slots = pages * kBinPageEntries;
-    return slots / (kBinPageEntries + static_cast<uint64_t>(nbins) * (align - 1)) * kBinPageEntries;
+    return slots / (kBinPadChunk + static_cast<uint64_t>(nbins) * (align - 1)) * kBinPadChunk;
 }
 
 void Engine::bin_free(Pass& p)
@@ -147,7 +154,7 @@ Status Engine::bin_append(Pass& p, const uint8_t* mask, const double* dx, const 
         bt.open_page = b.open_page;
         bt.open_fill = b.open_fill;
         CU_TRY(launch_bin_scatter(compute_, mask ? mask + done : nullptr, dx + done, dy + done, c2, cnt, gp_, p.layout, bt,
-                                  d_touched_, b.grid));
+                                  d_touched_, b.grid, b.threads));
         ++launches_;
         b.pending += cnt;
         done += cnt;

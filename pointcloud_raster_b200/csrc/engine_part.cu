@@ -95,6 +95,9 @@ Status Engine::partition_setup()
         cudaFree(d);
         for (size_t i = 0; i < passes_.size(); ++i) {
             BinState& b = passes_[i].bin;
+            // the chains were sized for the single-GPU scatter grid (more, smaller CTAs): a prefix of them is used here
+            b.threads = kBinThreadsPeer;
+            b.grid = std::min(b.grid, bin_scatter_grid(sm_count_, b.nbins, passes_[i].layout.n_chan, b.threads));
             const uint64_t chains = static_cast<uint64_t>(b.grid) * b.nbins;
             // Every source rank owns a fixed slice of every owner's pool and allocates pages from it with a counter
             // in its OWN memory: no remote atomic anywhere.  A slice must take all the points a rank may send
@@ -154,7 +157,7 @@ Status Engine::part_append(Pass& p, const uint8_t* mask, const double* dx, const
     bt.nbins = b.nbins;
     bt.open_page = b.open_page;
     bt.open_fill = b.open_fill;
-    CU_TRY(launch_bin_scatter(compute_, mask, dx, dy, ch, n, gp_, p.layout, bt, d_touched_, b.grid));
+    CU_TRY(launch_bin_scatter(compute_, mask, dx, dy, ch, n, gp_, p.layout, bt, d_touched_, b.grid, b.threads));
     ++launches_;
     b.pending += n;
     return Status::success();
