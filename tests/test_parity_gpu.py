@@ -364,6 +364,31 @@ def test_deterministic_mode_bit_reproducible(gpu_pcr, oracle):
     assert np.array_equal(got[0], ref, equal_nan=True)
 
 
+def test_deterministic_mode_hot_cells_in_order(gpu_pcr, oracle):
+    """Runs far longer than what one thread folds on its own (cells holding 150 000 and 40 000 points, one run
+    crossing many CTAs): the warp-assisted fold must still add in original point order — Sum equal to the
+    oracle's in-order fold bit for bit, over two ingests."""
+    pcr = gpu_pcr
+    gc = make_grid(pcr, 64, 64, tile=32)
+    rng = np.random.default_rng(11)
+    n_hot, n_warm, n_rest = 150_000, 40_000, 110_000
+    x = np.concatenate([np.full(n_hot, 10.25), rng.uniform(40.0, 41.0, n_warm), rng.uniform(0, 64, n_rest)])
+    y = np.concatenate([np.full(n_hot, 20.75), rng.uniform(7.0, 8.0, n_warm), rng.uniform(0, 64, n_rest)])
+    v = rng.normal(0, 100, len(x)).astype(np.float32)            # cancellation: the order of the adds shows
+    perm = rng.permutation(len(x))
+    x, y, v = x[perm], y[perm], v[perm]
+    R = pcr.ReductionType
+    specs = [spec(pcr, "value", t) for t in (R.Sum, R.Max, R.Min, R.Count, R.Average)]
+    clouds = [(x, y, {"value": v}), (x[::2], y[::2], {"value": v[::2]})]
+    gd = grid_desc(gc)
+    ref = oracle.run(gd, clouds, specs)
+    got, _ = run_product(pcr, gc, clouds, specs, deterministic=True)
+    for i in range(len(specs)):
+        assert np.array_equal(got[i], ref[i], equal_nan=True), f"band {i} differs from the in-order fold"
+    again, _ = run_product(pcr, gc, clouds, specs, deterministic=True)
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(got, again))
+
+
 # ---- full-size properties (BASELINE config 2: 5M points, 1000x1000) ------------------------------
 def test_full_size_point_config(gpu_pcr, oracle):
     gc = make_grid(gpu_pcr, 1000, 1000)
