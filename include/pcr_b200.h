@@ -121,7 +121,9 @@ typedef struct pcr_pipeline_desc {
                                                        ingest and folded bin by bin at finalize */
     int32_t                   warp_aggregate;       /* 0 = auto (adaptive run aggregation), 2 = off */
     int32_t                   gaussian_kernel;      /* 0 = auto, 1 = scatter (warp per point, REDs),
-                                                       2 = gather (tile-binned, atomic-free, deterministic) */
+                                                       2 = gather (tile-binned, atomic-free, deterministic),
+                                                       3 = per-bin GEMM (unrotated footprints, radius cap <= 32
+                                                       cells; what auto picks there unless deterministic) */
     int32_t                   comm_mode;            /* N>1 combine: 0 = auto (peer memory over NVLink when every
                                                        GPU pair has P2P access, else NCCL), 1 = NCCL, 2 = peer */
     int32_t                   comm_root_only;       /* N>1, where the finalized bands end up: 0 = complete on every

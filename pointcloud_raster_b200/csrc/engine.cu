@@ -824,12 +824,21 @@ bool Engine::use_gather(const Pass& p) const
     if (p.glyph.type != PCR_GLYPH_GAUSSIAN || !gauss_gather_supported(p.layout)) return false;
     if (exact_) return false;          // mode 2: the scatter kernel's per-cell contributions are summed exactly
     if (gaussian_variant_ == 1) return false;
-    if (gaussian_variant_ == 2) return true;
+    if (gaussian_variant_ == 2 || gaussian_variant_ == 3) return true;
     // auto: the gather needs footprints wide enough to amortise its per-(point,tile) tables.  Measured
     // on B200, 5M points, 1000x1000 (kernel scope): sigma=16 (r=32) gather 17.3 ms vs scatter 58 ms;
     // sigma=4 (r=12) 6.9 vs 11.1 ms; below ~r=4 the scatter's few REDs per point win.  The radius cap
     // is the only bound known at plan time.
     return deterministic_ || p.glyph.max_radius_cells >= 8.0f;
+}
+
+// Behind the same keys / sort / records front end: the per-bin GEMM (k_gauss_binmma) where it applies and
+// bit-reproducibility was not asked for, else the tile gather.  gaussian_kernel = 2 forces the tile gather.
+bool Engine::use_bin_mma(const Pass& p) const
+{
+    if (deterministic_ || gaussian_variant_ == 2) return false;
+    const bool rotated = !p.glyph.rotation_channel.empty() || p.glyph.default_rotation != 0.0f;
+    return gauss_binmma_supported(p.layout, p.glyph.max_radius_cells, rotated);
 }
 
 Status Engine::ensure_gauss_scratch(size_t n, size_t record_bytes)
@@ -941,8 +950,8 @@ Status Engine::run_passes(const double* dx, const double* dy, size_t n,
                     if (g2.sigma_y) g2.sigma_y += q0;
                     if (g2.rotation) g2.rotation += q0;
                     CU_TRY(launch_gaussian_gather(compute_, mask ? mask + q0 : nullptr, dx + q0, dy + q0, c2, g2, cnt, p.d_state, gp_, p.layout,
-                                                  d_touched_, gs_, sm_count_));
-                    launches_ += 4;   // keys, sort, records, gather
+                                                  d_touched_, gs_, sm_count_, use_bin_mma(p)));
+                    launches_ += 4;   // keys, sort, records, gather / per-bin GEMM
                 }
             } else
                 CU_TRY(launch_gaussian_accumulate(compute_, mask, dx, dy, ch, g, n, p.d_state, gp_, p.layout, d_touched_));

@@ -160,7 +160,8 @@ size_t gauss_record_bytes(const PassLayout& L);
 size_t gauss_sort_temp_bytes(size_t n, const GridParams& g);
 cudaError_t launch_gaussian_gather(cudaStream_t s, const uint8_t* mask, const double* x, const double* y, const ChannelPtrs& ch,
                                    const GlyphParams& gp, size_t n, uint32_t* state, const GridParams& g,
-                                   const PassLayout& L, uint32_t* touched, GaussScratch& sc, int sm_count);
+                                   const PassLayout& L, uint32_t* touched, GaussScratch& sc, int sm_count, bool bin_mma);
+bool gauss_binmma_supported(const PassLayout& L, float max_radius_cells, bool rotated);
 
 class Engine {
 public:
@@ -319,6 +320,7 @@ private:
     int gaussian_variant_ = 0;       // 0 auto, 1 scatter (warp per point), 2 gather
     Status ensure_gauss_scratch(size_t n, size_t record_bytes);
     bool use_gather(const Pass& p) const;
+    bool use_bin_mma(const Pass& p) const;
 
     // ---- stats / progress ----
     uint64_t collections_ = 0, points_ = 0;

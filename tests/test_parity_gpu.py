@@ -226,7 +226,7 @@ def test_line_flip_rate(gpu_pcr, oracle):
     assert flips <= max(2.0, 1e-6 * painted)
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["scatter", "gather"])
+@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["scatter", "gather", "bin_gemm"])
 def test_gaussian_vs_oracle(gpu_pcr, oracle, kernel):
     gc = make_grid(gpu_pcr, 160, 120, tile=64)
     rng = np.random.default_rng(21)
@@ -260,7 +260,8 @@ def test_gaussian_gather_edge_cases(gpu_pcr, oracle):
         s1 = gpu_pcr.gaussian_splat_spec("value", default_sigma=sig, max_radius_cells=cap)
         s2 = gpu_pcr.gaussian_splat_spec("value", default_sigma=sig, max_radius_cells=cap)
         s2.type = gpu_pcr.ReductionType.Count
-        for knobs in ({"gaussian_kernel": 2}, {"gaussian_kernel": 2, "ring_slot_points": 1024}):
+        for knobs in ({"gaussian_kernel": 2}, {"gaussian_kernel": 2, "ring_slot_points": 1024},
+                      {"gaussian_kernel": 3}, {"gaussian_kernel": 3, "ring_slot_points": 1024}):
             check_vs_oracle(gpu_pcr, oracle, gc, [(x, y, ch)], [s1, s2], f"gather {w}x{h} cap={cap} {knobs}",
                             device_weights=True, **knobs)
 
@@ -466,6 +467,15 @@ def test_full_size_gaussian_config(gpu_pcr, sigma):
     again, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs, gaussian_kernel=2)
     for a, b in zip(gather, again):
         assert np.array_equal(a, b, equal_nan=True)
+    # the per-bin GEMM (the default kernel for this configuration): same bounds against the scatter kernel
+    gemm, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs, gaussian_kernel=3)
+    auto, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs)
+    for got in (gemm, auto):
+        for k in (0, 1):
+            assert (np.abs(scatter[k].astype(np.float64) - got[k]) <= tol).all(), (sigma, k, "bin gemm")
+        assert np.array_equal(got[2], (got[0] / got[1]).astype(np.float32))
+        assert got[2].min() >= 0.0 and got[2].max() < 1.0
+        assert abs(got[1].astype(np.float64).sum() - total) <= 1e-6 * total
 
 
 # BASELINE config 4 against the ORACLE (not kernel against kernel): the first 200k points of the config-4 cloud,
@@ -494,7 +504,7 @@ def test_config4_subsample_vs_oracle(gpu_pcr, oracle, sigma):
                 self.c[k] = self.o.bounds(gd_, clouds_, s_, want_weight=want_weight)
             return self.c[k]
     memo = Memo(oracle)
-    for kernel, name in ((1, "scatter"), (2, "gather")):
+    for kernel, name in ((1, "scatter"), (2, "gather"), (3, "bin_gemm")):
         got, _ = run_product(gpu_pcr, gc, [(x, y, ch)], specs, gaussian_kernel=kernel)
         compare_bands(memo, gd, [(x, y, ch)], specs, ref, got, f"config 4 sigma={sigma} {name}", device_weights=True)
 

@@ -75,7 +75,7 @@ def _random_case(pcr, seed):
     if rng.random() < 0.3:
         knobs["ring_slot_points"] = int(rng.choice([1024, 4096]))
     if rng.random() < 0.3:
-        knobs["gaussian_kernel"] = int(rng.choice([1, 2]))
+        knobs["gaussian_kernel"] = int(rng.choice([1, 2, 3]))
     if rng.random() < 0.2:
         knobs["point_kernel"] = 2
     loc = [pcr.MemoryLocation.Host, pcr.MemoryLocation.HostPinned, pcr.MemoryLocation.Device][int(rng.integers(0, 3))]
