@@ -568,7 +568,7 @@ def leg_per_glyph(pcr, device):
                      "gcells_per_s": round(painted / (acc * 1e-3) / 1e9, 2) if painted else None}
     out["_scope"] = ("5M points, 1000x1000 grid; kernel scope = device-resident ingest + finalize_device, CUDA events; "
                      "e2e = pinned host cloud -> ingest -> finalize -> host band, wall clock; limiting unit: Point and Line "
-                     "the L2 reduction-request rate (profiles/), Gaussian gather instruction issue")
+                     "the L2 reduction-request rate (profiles/), Gaussian (per-bin GEMM, k_gauss_binmma) tensor pipe + table construction")
     return out
 
 
