@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import sys
+import weakref
 
 import numpy as np
 
@@ -737,7 +738,11 @@ class Pipeline:
         self._h = handle
         self._cfg = cfg
         self._keep = keep            # C strings / arrays referenced by the desc
-        self._result = None
+        # The result Grid (and every band view) keeps the Pipeline alive — the pinned result memory belongs to
+        # it, as with pybind11's reference_internal upstream — so the Pipeline must NOT hold the Grid strongly:
+        # that cycle would leave the device memory of every finalized pipeline to the cyclic garbage collector.
+        self._result_ref = None
+        self._has_result = False
         self._cb = None
 
     @staticmethod
@@ -890,16 +895,19 @@ class Pipeline:
             check(lib.pcr_pipeline_band_name(self._h, i, name, 512))
             bands.append(BandDesc(name.value.decode(), DataType.Float32, False))
         g = self._cfg.grid
-        self._result = Grid(g.width, g.height, bands, arrays, owner=self)
+        grid = Grid(g.width, g.height, bands, arrays, owner=self)
+        self._result_ref = weakref.ref(grid)
+        self._has_result = True
+        return grid
 
     def finalize(self):
         check(lib.pcr_pipeline_finalize(self._h))
-        self._wrap_result()
+        grid = self._wrap_result()
         if self._cfg.output_path:
             opts = GeoTiffOptions()
             opts.compress = "DEFLATE" if self._cfg.write_cog else "NONE"
             opts.cloud_optimized = bool(self._cfg.write_cog)
-            write_geotiff(self._cfg.output_path, self._result, self._cfg.grid, opts)
+            write_geotiff(self._cfg.output_path, grid, self._cfg.grid, opts)
 
     def finalize_device(self):
         """New: finalize into HBM only (no D2H); see result_band_device_ptr()."""
@@ -930,7 +938,12 @@ class Pipeline:
         check(lib.pcr_pipeline_set_progress_callback(self._h, self._cb, None))
 
     def result(self):
-        return self._result
+        """Grid over the pipeline's pinned host result (None before the first finalize()); the Grid and its
+        band views keep the pipeline alive, not the other way round."""
+        if not self._has_result:
+            return None
+        grid = self._result_ref() if self._result_ref is not None else None
+        return grid if grid is not None else self._wrap_result()
 
     def stats(self):
         p = _lib.Progress()
@@ -940,7 +953,8 @@ class Pipeline:
     # -- new-path extras ----------------------------------------------------
     def reset(self):
         check(lib.pcr_pipeline_reset(self._h))
-        self._result = None
+        self._result_ref = None
+        self._has_result = False
 
     def save_state(self, directory):
         """Write the accumulated state as reference-format .pcrt tile files (one per touched tile per

@@ -39,3 +39,18 @@ def gpu_pcr(pcr):
     -m gpu tests must never pass on a fallback."""
     assert pcr.device_count() > 0, "GPU test selected but no CUDA device is visible"
     return pcr
+
+
+@pytest.fixture(autouse=True)
+def _mem_trace(request):
+    """PCR_MEM_TRACE=<file>: free HBM before every GPU test (finds pipelines that outlive their test)."""
+    path = os.environ.get("PCR_MEM_TRACE")
+    if path and request.node.get_closest_marker("gpu"):
+        try:
+            from pointcloud_raster_b200 import pcr as _pcr
+            free, total = _pcr.device_mem_info()
+            with open(path, "a") as f:
+                f.write(f"{free / 2**30:8.1f} GB free  {request.node.nodeid}\n")
+        except Exception:
+            pass
+    yield

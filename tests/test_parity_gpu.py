@@ -289,6 +289,35 @@ def test_glyph_with_max_is_not_implemented(gpu_pcr):
         p.ingest(mk(gpu_pcr, [1.0], [1.0], {"value": [1.0]}))
 
 
+def test_pipeline_memory_released_without_gc(gpu_pcr):
+    """A finalized pipeline must give its device memory back when the last reference goes — by reference
+    counting, not by the cyclic garbage collector (result Grid and band views keep the pipeline alive, the
+    pipeline does not keep them)."""
+    import gc
+    pcr = gpu_pcr
+    gc.collect()
+    gc.disable()
+    try:
+        free0, _ = pcr.device_mem_info()
+        g = make_grid(pcr, 3000, 3000)
+        x, y, ch = uniform_cloud(200_000, 3000, 3000, seed=1)
+        s = spec(pcr, "value", pcr.ReductionType.Sum)
+        for _ in range(3):
+            got, p = run_product(pcr, g, [(x, y, ch)], [s], point_kernel=3, bin_pool_points=60_000_000)
+            grid = p.result()
+            assert grid is p.result()                        # one wrapper while somebody holds it
+            view = grid.band_array(0)
+            del p, grid                                      # the view alone keeps the pinned result alive
+            assert np.array_equal(view, got[0], equal_nan=True)
+            held, _ = pcr.device_mem_info()
+            assert free0 - held > 300 << 20                  # ... and with it the pipeline (pool + records + bands)
+            del view, got
+        free1, _ = pcr.device_mem_info()
+        assert free0 - free1 < 64 << 20, f"{(free0 - free1) >> 20} MB still held after the pipelines went out of scope"
+    finally:
+        gc.enable()
+
+
 # ---- API behaviour ---------------------------------------------------------------------------
 def test_error_behaviour(gpu_pcr):
     from util import cloud as mk
