@@ -221,6 +221,22 @@ def main():
          "Point + Line + Gaussian reductions side by side in one pipeline")
 
 
+def wide_gaussian_fixture():
+    """Footprint radii beyond 16 cells (sigma up to 12, cap 32): 65 x 65-cell footprints across several
+    reference tiles — the range the per-bin GEMM kernel covers with its 96-cell neighbourhood.  Own rng: added
+    after the other fixtures were generated, which keep their random streams."""
+    rng = np.random.default_rng(2026)
+    w, h, n = 160, 128, 500
+    x, y = rng.uniform(-1, w + 1, n), rng.uniform(-1, h + 1, n)
+    x[:6] = [0.0, w, w / 2, 63.999, 64.0, 64.001]
+    y[:6] = [0.0, h, h, 64.0, 63.999, 0.25]
+    ch = {"v": rng.uniform(-1, 1, n).astype(np.float32), "s": rng.uniform(3.0, 12.0, n).astype(np.float32)}
+    save("gauss_wide_sigma_tiles64", orc.GridDesc(0, 0, w, h, tile_width=64, tile_height=64), [(x, y, ch)],
+         [Spec("v", t, type=GAUSS, sigma_x_channel="s", sigma_y_channel="s", default_sigma_x=4.0,
+               default_sigma_y=4.0, max_radius_cells=32.0) for t in (WAVG, SUM, COUNT)],
+         "wide Gaussians (radius 9..32 cells) clipped at 64-cell reference tile seams")
+
+
 def pcrt_fixtures():
     """Reference-written .pcrt tile-state files (the reference flushes every dirty tile to state_dir at
     finalize, tile_manager.cpp:416-426): one single-reduction pipeline per op, so that one file name per
@@ -272,8 +288,12 @@ def pcrp_fixture():
 
 
 if __name__ == "__main__":
+    if "--wide-gauss-only" in sys.argv:
+        wide_gaussian_fixture()
+        sys.exit(0)
     if "--pcrt-only" not in sys.argv and "--io-only" not in sys.argv:
         main()
+        wide_gaussian_fixture()
     if "--io-only" not in sys.argv:
         pcrt_fixtures()
     pcrp_fixture()
