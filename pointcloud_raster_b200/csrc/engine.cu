@@ -825,10 +825,10 @@ bool Engine::use_gather(const Pass& p) const
     if (exact_) return false;          // mode 2: the scatter kernel's per-cell contributions are summed exactly
     if (gaussian_variant_ == 1) return false;
     if (gaussian_variant_ == 2 || gaussian_variant_ == 3) return true;
-    // auto: the gather needs footprints wide enough to amortise its per-(point,tile) tables.  Measured
-    // on B200, 5M points, 1000x1000 (kernel scope): sigma=16 (r=32) gather 17.3 ms vs scatter 58 ms;
-    // sigma=4 (r=12) 6.9 vs 11.1 ms; below ~r=4 the scatter's few REDs per point win.  The radius cap
-    // is the only bound known at plan time.
+    // auto: the sorted paths (per-bin GEMM, tile gather) need footprints wide enough to amortise their per-point
+    // tables.  Measured on B200, 5M points, 1000x1000 (kernel scope): sigma=16 (r=32) per-bin GEMM 5.4 ms, tile
+    // gather 11.7 ms, scatter 58 ms; sigma=4 (r=12) 3.2 / 5.0 / 11.1 ms; below ~r=4 the scatter's few REDs per
+    // point win.  The radius cap is the only bound known at plan time.
     return deterministic_ || p.glyph.max_radius_cells >= 8.0f;
 }
 
